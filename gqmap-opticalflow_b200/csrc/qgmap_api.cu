@@ -1,0 +1,685 @@
+// qgmap_api.cu -- C ABI of libqgmap.so (include/qgmap.h): handle management, layout conversion at the boundary,
+// iteration launches (CUDA graph of identical kernel nodes), monitoring, the one-call solver.
+#include "../../include/qgmap.h"
+#include "qgmap_iter.cuh"
+#include "qgmap_internal.h"
+#include "qgmap_layout.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+static thread_local std::string g_last_error;
+thread_local long long g_solve_launches = 0;
+thread_local float g_solve_ms = 0.f;
+
+#define QG_FAIL(h, code, ...)                                                        \
+    do {                                                                             \
+        char _b[512];                                                                \
+        snprintf(_b, sizeof _b, __VA_ARGS__);                                        \
+        if (h) (h)->err = _b;                                                        \
+        g_last_error = _b;                                                           \
+        return (code);                                                               \
+    } while (0)
+
+#define QG_CUDA(h, expr)                                                             \
+    do {                                                                             \
+        cudaError_t _e = (expr);                                                     \
+        if (_e != cudaSuccess)                                                       \
+            QG_FAIL(h, QGMAP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char *qgmap_last_error(const qgmap_handle *h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+extern "C" int qgmap_config_defaults(qgmap_config *c, int variant)
+{
+    if (!c || (variant != QGMAP_VARIANT_FULL && variant != QGMAP_VARIANT_SUPER)) return QGMAP_ERR_ARG;
+    std::memset(c, 0, sizeof *c);
+    c->struct_size = (int32_t)sizeof *c;
+    c->variant = variant;
+    c->L = 1; c->K = 3;
+    c->lambdad = 1.0; c->epsn = 1e-6;
+    const bool sup = variant == QGMAP_VARIANT_SUPER;
+    c->lambdas = sup ? 16.0 : 5.0;                 // optical_flowSuper.m:22 / optical_flow.m:19
+    c->temperature = sup ? 0.2 : 0.0;              // optical_flowSuper.m:25 / optical_flow.m:22
+    c->drate = sup ? 0.75 : 0.5;
+    c->minu = c->minv = -1.0; c->maxu = c->maxv = 1.0;
+    c->sigma_min = 0.01; c->sigma_max = sup ? 25.0 : 23.0;
+    c->corr_tor = 1.0 - 1e-5;
+    c->step0 = sup ? 0.001 : 0.1; c->step_tau = sup ? 4000.0 : 8000.0;
+    c->alpha_scale = 1e-7; c->T_floor = 0.001; c->tor = 1e-4;
+    c->alpha_start = 500; c->alpha_mode = QGMAP_ALPHA_SOFTMAX;
+    c->anneal_every = sup ? 500 : 0;
+    c->device = -1; c->row_begin = 0; c->row_end = 0; c->log_every = 300;
+    return QGMAP_OK;
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+template <int KT, bool SUPER, bool DUMP>
+static void launch_inst(const qgmap_handle *h) {
+    qgmap_iter_kernel<KT, SUPER, DUMP><<<h->grid, dim3(QG_TW, QG_TH + 1), 0, h->stream>>>(h->params);
+}
+template <bool SUPER, bool DUMP>
+static void launch_k(const qgmap_handle *h) {
+    switch (h->K) {
+        case 3: launch_inst<3, SUPER, DUMP>(h); break;
+        case 5: launch_inst<5, SUPER, DUMP>(h); break;
+        case 7: launch_inst<7, SUPER, DUMP>(h); break;
+        case 9: launch_inst<9, SUPER, DUMP>(h); break;
+        case 11: launch_inst<11, SUPER, DUMP>(h); break;
+        default: launch_inst<0, SUPER, DUMP>(h); break;
+    }
+}
+void qgmap_launch_iteration(const qgmap_handle *h);
+static void launch_iter(const qgmap_handle *h, bool dump) {
+    const bool sup = h->cfg.variant == QGMAP_VARIANT_SUPER;
+    if (sup) { if (dump) launch_k<true, true>(h); else launch_k<true, false>(h); }
+    else     { if (dump) launch_k<false, true>(h); else launch_k<false, false>(h); }
+}
+
+static int device_check(qgmap_handle *h, int device, int *dev_out)
+{
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        QG_FAIL(h, QGMAP_ERR_CUDA, "no CUDA device available (%s); libqgmap has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    int dev = device;
+    if (dev < 0) QG_CUDA(h, cudaGetDevice(&dev));
+    if (dev >= ndev) QG_FAIL(h, QGMAP_ERR_ARG, "device %d out of range (%d devices)", dev, ndev);
+    QG_CUDA(h, cudaSetDevice(dev));
+    *dev_out = dev;
+    return QGMAP_OK;
+}
+
+static void free_handle(qgmap_handle *h)
+{
+    if (!h) return;
+    if (h->device >= 0) cudaSetDevice(h->device);
+    qgmap_band_release(h);
+    if (h->graph) cudaGraphExecDestroy(h->graph);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    void *ptrs[] = {h->I1f, h->VVf, h->I1d, h->VVd, h->buf[0], h->buf[1], h->dbg, h->ctrl, h->partials, h->hist[0],
+                    h->hist[1], h->hist[2], h->stage, h->mon_partials, h->d_map, h->d_tflow, h->d_unknown};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+static int ensure_stage(qgmap_handle *h, size_t doubles)
+{
+    if (doubles <= h->stage_cap) return QGMAP_OK;
+    if (h->stage) { QG_CUDA(h, cudaFree(h->stage)); h->stage = nullptr; h->stage_cap = 0; }
+    QG_CUDA(h, cudaMalloc(&h->stage, doubles * sizeof(double)));
+    h->stage_cap = doubles;
+    return QGMAP_OK;
+}
+
+static int ensure_hist(qgmap_handle *h, int its)
+{
+    if (its <= h->hist_cap) return QGMAP_OK;
+    int cap = std::max(its, 1024);
+    for (int k = 0; k < 3; ++k) {
+        double *n = nullptr;
+        QG_CUDA(h, cudaMalloc(&n, (size_t)cap * sizeof(double)));
+        QG_CUDA(h, cudaMemsetAsync(n, 0, (size_t)cap * sizeof(double), h->stream));
+        if (h->hist[k]) {
+            QG_CUDA(h, cudaMemcpyAsync(n, h->hist[k], (size_t)h->hist_cap * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+            QG_CUDA(h, cudaStreamSynchronize(h->stream));
+            QG_CUDA(h, cudaFree(h->hist[k]));
+        }
+        h->hist[k] = n;
+    }
+    h->hist_cap = cap;
+    h->params.hist_energy = h->hist[0]; h->params.hist_dmu = h->hist[1]; h->params.hist_dsig = h->hist[2];
+    if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }     // params are baked into graph nodes
+    return QGMAP_OK;
+}
+
+extern "C" int qgmap_create(const qgmap_config *cfg, const double *I1, const double *I2, int Mo, int No, qgmap_handle **out)
+{
+    if (!cfg || !I1 || !I2 || !out) QG_FAIL((qgmap_handle *)nullptr, QGMAP_ERR_ARG, "qgmap_create: NULL argument");
+    *out = nullptr;
+    if (cfg->struct_size != (int32_t)sizeof(qgmap_config))
+        QG_FAIL((qgmap_handle *)nullptr, QGMAP_ERR_ARG, "qgmap_config.struct_size %d != %zu (ABI mismatch)", cfg->struct_size, sizeof(qgmap_config));
+    const bool sup = cfg->variant == QGMAP_VARIANT_SUPER;
+    if (cfg->variant != QGMAP_VARIANT_FULL && !sup) QG_FAIL((qgmap_handle *)nullptr, QGMAP_ERR_ARG, "bad variant %d", cfg->variant);
+    if (cfg->L < 1 || cfg->L > QGMAP_LMAX) QG_FAIL((qgmap_handle *)nullptr, QGMAP_ERR_ARG, "L=%d out of range 1..%d", cfg->L, QGMAP_LMAX);
+    if (cfg->K < 1 || cfg->K > QGMAP_KMAX) QG_FAIL((qgmap_handle *)nullptr, QGMAP_ERR_ARG, "K=%d out of range 1..%d", cfg->K, QGMAP_KMAX);
+    if (Mo < 4 || No < 4) QG_FAIL((qgmap_handle *)nullptr, QGMAP_ERR_ARG, "image %dx%d too small (bicubic needs >=4x4)", Mo, No);
+    if (sup && (Mo % 4 || No % 4)) QG_FAIL((qgmap_handle *)nullptr, QGMAP_ERR_ARG, "super-pixel variant needs Mo,No divisible by 4 (got %dx%d)", Mo, No);
+    const int M = sup ? Mo / 4 : Mo, N = sup ? No / 4 : No;
+    if (M < 3 || N < 3) QG_FAIL((qgmap_handle *)nullptr, QGMAP_ERR_ARG, "belief grid %dx%d has no interior", M, N);
+    int rb = cfg->row_begin, re = cfg->row_end;
+    if (rb == 0 && re == 0) re = M;
+    if (rb < 0 || re > M || rb >= re) QG_FAIL((qgmap_handle *)nullptr, QGMAP_ERR_ARG, "bad row band [%d,%d) of %d", rb, re, M);
+
+    qgmap_handle *h = new qgmap_handle();
+    h->cfg = *cfg;
+    h->Mo = Mo; h->No = No; h->M = M; h->N = N; h->L = cfg->L; h->K = cfg->K;
+    int rc = device_check(h, cfg->device, &h->device);
+    if (rc) { g_last_error = h->err; delete h; return rc; }
+#define QG_CUDA_C(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { \
+        char _b[512]; snprintf(_b, sizeof _b, "%s failed: %s", #expr, cudaGetErrorString(_e)); g_last_error = _b; free_handle(h); return QGMAP_ERR_CUDA; } } while (0)
+    QG_CUDA_C(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    QG_CUDA_C(cudaEventCreate(&h->ev0));
+    QG_CUDA_C(cudaEventCreate(&h->ev1));
+
+    // rows stored locally: owned band plus one halo row on each side (clipped to the grid)
+    h->row_begin = rb; h->row_end = re;
+    h->g0 = std::max(rb - 1, 0); h->g1 = std::min(re + 1, M);
+    h->rows_local = h->g1 - h->g0;
+    h->out_r0 = std::max(rb, 1); h->out_r1 = std::min(re, M - 1);
+    h->P = (N + 31) / 32 * 32;
+    h->plane = (long long)h->rows_local * h->P;
+    const size_t state_floats = (size_t)F_COUNT * h->L * h->plane;
+    QG_CUDA_C(cudaMalloc(&h->buf[0], state_floats * sizeof(float)));
+    QG_CUDA_C(cudaMalloc(&h->buf[1], state_floats * sizeof(float)));
+    QG_CUDA_C(cudaMemsetAsync(h->buf[0], 0, state_floats * sizeof(float), h->stream));
+    QG_CUDA_C(cudaMemsetAsync(h->buf[1], 0, state_floats * sizeof(float), h->stream));
+
+    // images: fp64 row-major copies for monitoring, fp32 for the iteration kernel
+    h->pitchI = (No + 3) / 4 * 4; h->pitchV = (No + 2 + 3) / 4 * 4;
+    const size_t nI = (size_t)Mo * h->pitchI, nV = (size_t)(Mo + 2) * h->pitchV;
+    QG_CUDA_C(cudaMalloc(&h->I1d, nI * sizeof(double)));
+    QG_CUDA_C(cudaMalloc(&h->VVd, nV * sizeof(double)));
+    QG_CUDA_C(cudaMalloc(&h->I1f, nI * sizeof(float)));
+    QG_CUDA_C(cudaMalloc(&h->VVf, nV * sizeof(float)));
+    QG_CUDA_C(cudaMemsetAsync(h->I1d, 0, nI * sizeof(double), h->stream));
+    QG_CUDA_C(cudaMemsetAsync(h->VVd, 0, nV * sizeof(double), h->stream));
+    {
+        const size_t MoNo = (size_t)Mo * No;
+        QG_CUDA_C(cudaMalloc(&h->stage, MoNo * sizeof(double)));
+        h->stage_cap = MoNo;
+        dim3 tb(32, 8), tg((No + 31) / 32, (Mo + 31) / 32, 1);
+        QG_CUDA_C(cudaMemcpyAsync(h->stage, I1, MoNo * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        qgmap_import_kernel<double><<<tg, tb, 0, h->stream>>>(h->stage, Mo, No, 1, h->I1d, h->pitchI, 0, 0, Mo, 0);
+        QG_CUDA_C(cudaStreamSynchronize(h->stream));            // stage is reused for I2
+        QG_CUDA_C(cudaMemcpyAsync(h->stage, I2, MoNo * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        qgmap_vv_rows_kernel<<<(No + 2 + 127) / 128, 128, 0, h->stream>>>(h->stage, Mo, No, h->VVd, h->pitchV);
+        qgmap_vv_cols_kernel<<<(Mo + 2 + 127) / 128, 128, 0, h->stream>>>(Mo, No, h->VVd, h->pitchV);
+        qgmap_cast_kernel<float><<<256, 256, 0, h->stream>>>(h->I1d, h->I1f, (long long)nI);
+        qgmap_cast_kernel<float><<<256, 256, 0, h->stream>>>(h->VVd, h->VVf, (long long)nV);
+        QG_CUDA_C(cudaGetLastError());
+    }
+
+    // tiles
+    const int out_rows = std::max(h->out_r1 - h->out_r0, 0);
+    h->grid = dim3((N - 2 + QG_TW - 2) / (QG_TW - 1), std::max((out_rows + QG_TH - 1) / QG_TH, 1), h->L);
+    const size_t nblk = (size_t)h->grid.x * h->grid.y * h->grid.z;
+    QG_CUDA_C(cudaMalloc(&h->partials, nblk * QG_NRED * sizeof(double)));
+    QG_CUDA_C(cudaMemsetAsync(h->partials, 0, nblk * QG_NRED * sizeof(double), h->stream));
+    QG_CUDA_C(cudaMalloc(&h->ctrl, sizeof(QgCtrl)));
+    QG_CUDA_C(cudaMemsetAsync(h->ctrl, 0, sizeof(QgCtrl), h->stream));
+    QG_CUDA_C(cudaMallocHost(&h->ctrl_host, sizeof(QgCtrl)));
+    QG_CUDA_C(cudaMalloc(&h->mon_partials, 1024 * sizeof(double)));
+
+    // Gauss-Hermite tables (GaussHermite_2.m:21-32; gqmap_gpu_mixture.m:8-10)
+    double X[QGMAP_KMAX], W[QGMAP_KMAX];
+    if (qgmap_gauss_hermite(h->K, X, W) != QGMAP_OK) { g_last_error = "gauss_hermite failed"; free_handle(h); return QGMAP_ERR_ARG; }
+    QgIterParams &p = h->params;
+    std::memset(&p, 0, sizeof p);
+    for (int k = 0; k < h->K; ++k) {
+        p.tab.X[k] = (float)X[k]; p.tab.W[k] = (float)W[k];
+        p.tab.WX[k] = (float)(W[k] * X[k]); p.tab.WXX[k] = (float)(W[k] * X[k] * X[k]);
+    }
+    p.I1 = h->I1f; p.pitchI = h->pitchI; p.VV = h->VVf; p.pitchV = h->pitchV;
+    p.buf[0] = h->buf[0]; p.buf[1] = h->buf[1];
+    p.plane = h->plane; p.P = h->P; p.M = M; p.N = N; p.L = h->L; p.Mo = Mo; p.No = No;
+    p.g0 = h->g0; p.out_r0 = h->out_r0; p.out_r1 = h->out_r1; p.K = h->K; p.band = 0;
+    p.lambdad = (float)cfg->lambdad; p.lambdas = (float)cfg->lambdas; p.epsn = (float)cfg->epsn;
+    p.minu = (float)cfg->minu; p.maxu = (float)cfg->maxu; p.minv = (float)cfg->minv; p.maxv = (float)cfg->maxv;
+    p.sig_min = (float)cfg->sigma_min; p.sig_max = (float)cfg->sigma_max; p.corr_tor = (float)cfg->corr_tor;
+    p.step0 = cfg->step0; p.step_tau = cfg->step_tau; p.alpha_scale = cfg->alpha_scale; p.drate = cfg->drate;
+    p.T_floor = cfg->T_floor; p.tor = cfg->tor; p.alpha_start = cfg->alpha_start; p.alpha_mode = cfg->alpha_mode;
+    p.anneal_every = cfg->anneal_every;
+    p.ctrl = h->ctrl; p.partials = h->partials;
+    QG_CUDA_C(cudaStreamSynchronize(h->stream));
+    if (ensure_hist(h, 1024) != QGMAP_OK) { free_handle(h); return QGMAP_ERR_CUDA; }
+    QG_CUDA_C(cudaStreamSynchronize(h->stream));
+#undef QG_CUDA_C
+    *out = h;
+    return QGMAP_OK;
+}
+
+extern "C" int qgmap_destroy(qgmap_handle *h)
+{
+    if (!h) return QGMAP_ERR_ARG;
+    free_handle(h);
+    return QGMAP_OK;
+}
+
+extern "C" int qgmap_dims(const qgmap_handle *h, int *M, int *N, int *L)
+{
+    if (!h) return QGMAP_ERR_ARG;
+    if (M) *M = h->M;
+    if (N) *N = h->N;
+    if (L) *L = h->L;
+    return QGMAP_OK;
+}
+
+// column-major fp64 host array (M x N x planes) -> fp32 planes [field_first .. ) of BOTH ping-pong buffers
+static int import_planes(qgmap_handle *h, const double *src, int planes, int plane_first)
+{
+    const size_t n = (size_t)h->M * h->N * planes;
+    int rc = ensure_stage(h, n);
+    if (rc) return rc;
+    QG_CUDA(h, cudaMemcpyAsync(h->stage, src, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    dim3 tb(32, 8), tg((h->N + 31) / 32, (h->rows_local + 31) / 32, planes);
+    for (int b = 0; b < 2; ++b)
+        qgmap_import_kernel<float><<<tg, tb, 0, h->stream>>>(h->stage, h->M, h->N, planes,
+                                                              h->buf[b] + (size_t)plane_first * h->plane, h->P, h->plane,
+                                                              h->g0, h->g1, h->g0);
+    QG_CUDA(h, cudaGetLastError());
+    QG_CUDA(h, cudaStreamSynchronize(h->stream));     // stage reused by the next call
+    return QGMAP_OK;
+}
+
+// fp32 planes of the CURRENT buffer -> column-major fp64 host array; only the owned rows [row_begin,row_end) are written
+static int export_planes(qgmap_handle *h, int cur, int planes, int plane_first, double *dst)
+{
+    const size_t n = (size_t)h->M * h->N * planes;
+    int rc = ensure_stage(h, n);
+    if (rc) return rc;
+    const bool whole = (h->row_begin == 0 && h->row_end == h->M);
+    if (!whole) QG_CUDA(h, cudaMemcpyAsync(h->stage, dst, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    dim3 tb(32, 8), tg((h->N + 31) / 32, (h->row_end - h->row_begin + 31) / 32, planes);
+    qgmap_export_kernel<float><<<tg, tb, 0, h->stream>>>(h->buf[cur] + (size_t)plane_first * h->plane, h->P, h->plane, h->g0,
+                                                          h->row_begin, h->row_end, h->stage, h->M, h->N);
+    QG_CUDA(h, cudaGetLastError());
+    QG_CUDA(h, cudaMemcpyAsync(dst, h->stage, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    QG_CUDA(h, cudaStreamSynchronize(h->stream));
+    return QGMAP_OK;
+}
+
+static int sync_ctrl(qgmap_handle *h)
+{
+    QG_CUDA(h, cudaMemcpyAsync(h->ctrl_host, h->ctrl, sizeof(QgCtrl), cudaMemcpyDeviceToHost, h->stream));
+    QG_CUDA(h, cudaStreamSynchronize(h->stream));
+    return QGMAP_OK;
+}
+
+extern "C" int qgmap_set_state(qgmap_handle *h, const double *muu, const double *muv, const double *sigu,
+                               const double *sigv, const double *pn, const double *rou, const double *w,
+                               const double *alpha, double T, int it)
+{
+    if (!h) return QGMAP_ERR_ARG;
+    if (!muu || !muv || !sigu || !sigv || !pn || !rou || !w) QG_FAIL(h, QGMAP_ERR_ARG, "qgmap_set_state: NULL array");
+    if (it < 1) QG_FAIL(h, QGMAP_ERR_ARG, "qgmap_set_state: it must be >= 1");
+    QG_CUDA(h, cudaSetDevice(h->device));
+    const int L = h->L;
+    const double *fields[5] = {muu, muv, sigu, sigv, pn};
+    int rc;
+    for (int f = 0; f < 5; ++f)
+        if ((rc = import_planes(h, fields[f], L, f * L)) != QGMAP_OK) return rc;
+    for (int q = 0; q < 4; ++q)     // rou(:,:,:,e,c): q = e + 2c is the slowest MATLAB dimension pair
+        if ((rc = import_planes(h, rou + (size_t)q * h->M * h->N * L, L, (F_ROU0 + q) * L)) != QGMAP_OK) return rc;
+    QgCtrl c;
+    std::memset(&c, 0, sizeof c);
+    // it odd -> current buffer 0; both buffers hold the same state after import, so any `it` is consistent
+    c.it = it; c.stop = 0; c.its = std::numeric_limits<int>::max(); c.ticket = 0; c.T = T;
+    double se = 0.0;
+    for (int l = 0; l < L; ++l) { c.w[l] = w[l]; se += std::exp(w[l]); }
+    for (int l = 0; l < L; ++l) c.alpha[l] = alpha ? alpha[l] : std::exp(w[l]) / se;      // :18
+    *h->ctrl_host = c;
+    QG_CUDA(h, cudaMemcpyAsync(h->ctrl, h->ctrl_host, sizeof c, cudaMemcpyHostToDevice, h->stream));
+    QG_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->has_state = true;
+    return qgmap_band_refresh(h);
+}
+
+extern "C" int qgmap_get_state(qgmap_handle *h, double *muu, double *muv, double *sigu, double *sigv, double *pn,
+                               double *rou, double *w, double *alpha, double *T, int *it)
+{
+    if (!h) return QGMAP_ERR_ARG;
+    if (!h->has_state) QG_FAIL(h, QGMAP_ERR_STATE, "qgmap_get_state: no state set");
+    QG_CUDA(h, cudaSetDevice(h->device));
+    int rc = sync_ctrl(h);
+    if (rc) return rc;
+    const QgCtrl &c = *h->ctrl_host;
+    const int cur = (c.it - 1) & 1, L = h->L;
+    double *fields[5] = {muu, muv, sigu, sigv, pn};
+    for (int f = 0; f < 5; ++f)
+        if (fields[f] && (rc = export_planes(h, cur, L, f * L, fields[f])) != QGMAP_OK) return rc;
+    if (rou)
+        for (int q = 0; q < 4; ++q)
+            if ((rc = export_planes(h, cur, L, (F_ROU0 + q) * L, rou + (size_t)q * h->M * h->N * L)) != QGMAP_OK) return rc;
+    for (int l = 0; l < L; ++l) { if (w) w[l] = c.w[l]; if (alpha) alpha[l] = c.alpha[l]; }
+    if (T) *T = c.T;
+    if (it) *it = c.it;
+    return QGMAP_OK;
+}
+
+// splitmix64 -> xoshiro256**
+struct Rng {
+    uint64_t s[4];
+    explicit Rng(uint64_t seed) { for (auto &v : s) { seed += 0x9E3779B97F4A7C15ULL; uint64_t z = seed; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL; z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL; v = z ^ (z >> 31); } }
+    static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+    uint64_t next() { uint64_t r = rotl(s[1] * 5, 7) * 9, t = s[1] << 17; s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = rotl(s[3], 45); return r; }
+    double uniform() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+};
+
+extern "C" int qgmap_init_state(qgmap_handle *h, uint64_t seed)
+{
+    if (!h) return QGMAP_ERR_ARG;
+    const size_t n = (size_t)h->M * h->N * h->L;
+    const qgmap_config &c = h->cfg;
+    std::vector<double> w(h->L), muu(n), muv(n), sigu(n), sigv(n), pn(n, 0.0), rou(n * 4, 0.0);
+    Rng r(seed);
+    for (auto &v : w) v = r.uniform();                                           // :18
+    for (auto &v : muu) v = c.minu + r.uniform() * (c.maxu - c.minu);            // :19
+    for (auto &v : muv) v = c.minv + r.uniform() * (c.maxv - c.minv);            // :20
+    for (auto &v : sigu) v = r.uniform() + (c.maxu - c.minu);                    // :21
+    for (auto &v : sigv) v = r.uniform() + (c.maxv - c.minv);                    // :22
+    return qgmap_set_state(h, muu.data(), muv.data(), sigu.data(), sigv.data(), pn.data(), rou.data(), w.data(), nullptr,
+                           c.temperature, 1);
+}
+
+static const int kGraphLen = 25;
+
+static int build_graph(qgmap_handle *h)
+{
+    if (h->graph || h->nranks > 1) return QGMAP_OK;
+    cudaGraph_t g = nullptr;
+    QG_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    for (int i = 0; i < kGraphLen; ++i) launch_iter(h, false);
+    QG_CUDA(h, cudaStreamEndCapture(h->stream, &g));
+    cudaError_t e = cudaGraphInstantiate(&h->graph, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) QG_FAIL(h, QGMAP_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    return QGMAP_OK;
+}
+
+extern "C" int qgmap_step(qgmap_handle *h, int n, int its, double *energy, double *ptdmu, double *ptdsigma,
+                          int *n_done, int *stopped)
+{
+    if (!h) return QGMAP_ERR_ARG;
+    if (n < 0 || its < 1) QG_FAIL(h, QGMAP_ERR_ARG, "qgmap_step: n=%d its=%d", n, its);
+    if (!h->has_state) QG_FAIL(h, QGMAP_ERR_STATE, "qgmap_step before qgmap_set_state/qgmap_init_state");
+    QG_CUDA(h, cudaSetDevice(h->device));
+    int rc = ensure_hist(h, its);
+    if (rc) return rc;
+    const int it0 = h->ctrl_host->it;
+    if (h->ctrl_host->its != its) {
+        h->ctrl_host->its = its;
+        // the reference tests `it > its` after incrementing: a run resumed past its stops after one more iteration
+        QG_CUDA(h, cudaMemcpyAsync(&h->ctrl->its, &h->ctrl_host->its, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    }
+    long long launches = 0;
+    QG_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    int left = n;
+    if (h->nranks > 1) {
+        for (; left > 0; --left) { if ((rc = qgmap_band_iteration(h, &launches)) != QGMAP_OK) return rc; }
+    } else {
+        if (left >= kGraphLen && (rc = build_graph(h)) != QGMAP_OK) return rc;
+        for (; left >= kGraphLen; left -= kGraphLen) { QG_CUDA(h, cudaGraphLaunch(h->graph, h->stream)); launches += kGraphLen; }
+        for (; left > 0; --left) { launch_iter(h, false); ++launches; }
+    }
+    QG_CUDA(h, cudaGetLastError());
+    QG_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    if ((rc = sync_ctrl(h)) != QGMAP_OK) return rc;
+    QG_CUDA(h, cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    h->last_launches = launches;
+    const int done = h->ctrl_host->it - it0;
+    if (n_done) *n_done = done;
+    if (stopped) *stopped = h->ctrl_host->stop;
+    double *dst[3] = {energy, ptdmu, ptdsigma};
+    for (int k = 0; k < 3; ++k)
+        if (dst[k] && done > 0)
+            QG_CUDA(h, cudaMemcpyAsync(dst[k], h->hist[k] + (it0 - 1), (size_t)done * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    QG_CUDA(h, cudaStreamSynchronize(h->stream));
+    return QGMAP_OK;
+}
+
+extern "C" int qgmap_last_step_ms(const qgmap_handle *h, float *ms)
+{
+    if (!h || !ms) return QGMAP_ERR_ARG;
+    *ms = h->last_ms;
+    return QGMAP_OK;
+}
+extern "C" int qgmap_last_launches(const qgmap_handle *h, long long *launches)
+{
+    if (!h || !launches) return QGMAP_ERR_ARG;
+    *launches = h->last_launches;
+    return QGMAP_OK;
+}
+
+// ---- monitoring ------------------------------------------------------------------------------------------------------
+static QgMonArgs mon_params(const qgmap_handle *h)
+{
+    QgMonArgs q;
+    q.I1 = h->I1d; q.pitchI = h->pitchI; q.VV = h->VVd; q.pitchV = h->pitchV;
+    q.Mo = h->Mo; q.No = h->No; q.M = h->M; q.N = h->N; q.super = h->cfg.variant == QGMAP_VARIANT_SUPER;
+    q.lambdad = h->cfg.lambdad; q.lambdas = h->cfg.lambdas; q.epsn = h->cfg.epsn;
+    return q;
+}
+
+static int ensure_map(qgmap_handle *h)
+{
+    if (!h->d_map) QG_CUDA(h, cudaMalloc(&h->d_map, (size_t)h->M * h->N * 2 * sizeof(double)));
+    return QGMAP_OK;
+}
+
+// MAP of the current beliefs into h->d_map (device, column-major M x N x 2)
+static int map_device(qgmap_handle *h)
+{
+    int rc = ensure_map(h);
+    if (rc) return rc;
+    if (h->nranks > 1) QG_FAIL(h, QGMAP_ERR_STATE, "qgmap_get_map on a band handle: gather the state and use qgmap_find_map");
+    const int cur = (h->ctrl_host->it - 1) & 1;
+    const float *b = h->buf[cur];
+    const long long fs = (long long)h->L * h->plane;
+    const long long tot = 2LL * h->M * h->N;
+    qgmap_launch_find_map_f32(&h->ctrl->alpha[0], b + F_MUU * fs, b + F_SIGU * fs, b + F_MUV * fs, b + F_SIGV * fs, h->plane,
+                              h->M, h->N, h->L, h->P, h->g0, h->d_map, tot, h->stream);
+    QG_CUDA(h, cudaGetLastError());
+    return QGMAP_OK;
+}
+
+extern "C" int qgmap_get_map(qgmap_handle *h, double *map)
+{
+    if (!h || !map) return QGMAP_ERR_ARG;
+    if (!h->has_state) QG_FAIL(h, QGMAP_ERR_STATE, "qgmap_get_map: no state set");
+    QG_CUDA(h, cudaSetDevice(h->device));
+    int rc = sync_ctrl(h);
+    if (rc) return rc;
+    if ((rc = map_device(h)) != QGMAP_OK) return rc;
+    QG_CUDA(h, cudaMemcpyAsync(map, h->d_map, (size_t)h->M * h->N * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    QG_CUDA(h, cudaStreamSynchronize(h->stream));
+    return QGMAP_OK;
+}
+
+static int reduce_partials(qgmap_handle *h, int nblk, double *out)
+{
+    std::vector<double> hp(nblk);
+    QG_CUDA(h, cudaMemcpyAsync(hp.data(), h->mon_partials, nblk * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    QG_CUDA(h, cudaStreamSynchronize(h->stream));
+    double s = 0.0;
+    for (double v : hp) s += v;
+    *out = s;
+    return QGMAP_OK;
+}
+
+static int logp_device(qgmap_handle *h, const double *d_map, double *lp)
+{
+    const int nblk = 592;    // 4 x 148 SMs
+    qgmap_launch_logp(mon_params(h), d_map, h->mon_partials, nblk, h->stream);
+    QG_CUDA(h, cudaGetLastError());
+    return reduce_partials(h, nblk, lp);
+}
+
+extern "C" int qgmap_logp(qgmap_handle *h, const double *map, double *lp)
+{
+    if (!h || !map || !lp) return QGMAP_ERR_ARG;
+    QG_CUDA(h, cudaSetDevice(h->device));
+    int rc = ensure_map(h);
+    if (rc) return rc;
+    QG_CUDA(h, cudaMemcpyAsync(h->d_map, map, (size_t)h->M * h->N * 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    return logp_device(h, h->d_map, lp);
+}
+
+static int upload_truth(qgmap_handle *h, const double *tflow, const uint8_t *unknown)
+{
+    const size_t MoNo = (size_t)h->Mo * h->No;
+    if (!h->d_tflow) QG_CUDA(h, cudaMalloc(&h->d_tflow, MoNo * 2 * sizeof(double)));
+    QG_CUDA(h, cudaMemcpyAsync(h->d_tflow, tflow, MoNo * 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    h->has_unknown = unknown != nullptr;
+    if (unknown) {
+        if (!h->d_unknown) QG_CUDA(h, cudaMalloc(&h->d_unknown, MoNo));
+        QG_CUDA(h, cudaMemcpyAsync(h->d_unknown, unknown, MoNo, cudaMemcpyHostToDevice, h->stream));
+    }
+    return QGMAP_OK;
+}
+
+static int aepe_device(qgmap_handle *h, const double *d_map, double *aepe)
+{
+    const int nblk = 592;
+    qgmap_launch_aepe(mon_params(h), d_map, h->d_tflow, h->has_unknown ? h->d_unknown : nullptr, h->mon_partials, nblk, h->stream);
+    QG_CUDA(h, cudaGetLastError());
+    double s;
+    int rc = reduce_partials(h, nblk, &s);
+    if (rc) return rc;
+    const int b = h->cfg.variant == QGMAP_VARIANT_SUPER ? 4 : 1;
+    *aepe = s / ((double)(h->Mo - 2 * b) * (double)(h->No - 2 * b));
+    return QGMAP_OK;
+}
+
+extern "C" int qgmap_aepe(qgmap_handle *h, const double *map, const double *tflow, const uint8_t *unknown, double *aepe)
+{
+    if (!h || !map || !tflow || !aepe) return QGMAP_ERR_ARG;
+    QG_CUDA(h, cudaSetDevice(h->device));
+    int rc = ensure_map(h);
+    if (rc) return rc;
+    if ((rc = upload_truth(h, tflow, unknown)) != QGMAP_OK) return rc;
+    QG_CUDA(h, cudaMemcpyAsync(h->d_map, map, (size_t)h->M * h->N * 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    return aepe_device(h, h->d_map, aepe);
+}
+
+extern "C" int qgmap_debug_gradients(qgmap_handle *h, double *G_muu, double *G_muv, double *G_sigu, double *G_sigv,
+                                     double *dpn, double *drou, double *e_px, double *da_px)
+{
+    if (!h) return QGMAP_ERR_ARG;
+    if (!h->has_state) QG_FAIL(h, QGMAP_ERR_STATE, "qgmap_debug_gradients: no state set");
+    QG_CUDA(h, cudaSetDevice(h->device));
+    const size_t nf = (size_t)11 * h->L * h->plane;
+    if (!h->dbg) QG_CUDA(h, cudaMalloc(&h->dbg, nf * sizeof(float)));
+    QG_CUDA(h, cudaMemsetAsync(h->dbg, 0, nf * sizeof(float), h->stream));
+    h->params.dbg = h->dbg;
+    launch_iter(h, true);
+    QG_CUDA(h, cudaGetLastError());
+    const int L = h->L;
+    const size_t n = (size_t)h->M * h->N * L;
+    int rc = ensure_stage(h, n);
+    if (rc) return rc;
+    double *outs[11] = {G_muu, G_muv, G_sigu, G_sigv, dpn, drou, drou ? drou + n : nullptr, drou ? drou + 2 * n : nullptr,
+                        drou ? drou + 3 * n : nullptr, e_px, da_px};
+    dim3 tb(32, 8), tg((h->N + 31) / 32, (h->row_end - h->row_begin + 31) / 32, L);
+    for (int f = 0; f < 11; ++f) {
+        if (!outs[f]) continue;
+        QG_CUDA(h, cudaMemsetAsync(h->stage, 0, n * sizeof(double), h->stream));
+        qgmap_export_kernel<float><<<tg, tb, 0, h->stream>>>(h->dbg + (size_t)f * L * h->plane, h->P, h->plane, h->g0,
+                                                              h->row_begin, h->row_end, h->stage, h->M, h->N);
+        QG_CUDA(h, cudaMemcpyAsync(outs[f], h->stage, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        QG_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    return QGMAP_OK;
+}
+
+// ---- stateless get_map_mex replacement ---------------------------------------------------------------------------------
+extern "C" int qgmap_find_map(const double *alpha, const double *mu_u, const double *sig_u, const double *mu_v,
+                              const double *sig_v, int M, int N, int L, double *map, int device)
+{
+    qgmap_handle *nh = nullptr;
+    if (!alpha || !mu_u || !sig_u || !mu_v || !sig_v || !map) QG_FAIL(nh, QGMAP_ERR_ARG, "qgmap_find_map: NULL argument");
+    if (M < 1 || N < 1 || L < 1 || L > QGMAP_LMAX) QG_FAIL(nh, QGMAP_ERR_ARG, "qgmap_find_map: bad size M=%d N=%d L=%d (L<=%d)", M, N, L, QGMAP_LMAX);
+    int dev;
+    int rc = device_check(nh, device, &dev);
+    if (rc) return rc;
+    const size_t n = (size_t)M * N * L, MN = (size_t)M * N;
+    double *d = nullptr;
+    QG_CUDA(nh, cudaMalloc(&d, (4 * n + 2 * MN + QGMAP_LMAX) * sizeof(double)));
+    double *d_mu_u = d, *d_sig_u = d + n, *d_mu_v = d + 2 * n, *d_sig_v = d + 3 * n, *d_map = d + 4 * n, *d_alpha = d_map + 2 * MN;
+    cudaError_t e = cudaSuccess;
+    auto cp = [&](double *dst, const double *src, size_t cnt) { if (e == cudaSuccess) e = cudaMemcpy(dst, src, cnt * sizeof(double), cudaMemcpyHostToDevice); };
+    cp(d_mu_u, mu_u, n); cp(d_sig_u, sig_u, n); cp(d_mu_v, mu_v, n); cp(d_sig_v, sig_v, n); cp(d_alpha, alpha, L);
+    if (e == cudaSuccess) {
+        qgmap_launch_find_map_f64(d_alpha, d_mu_u, d_sig_u, d_mu_v, d_sig_v, (long long)MN, M, N, L, d_map, 2LL * MN, 0);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(map, d_map, 2 * MN * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) QG_FAIL(nh, QGMAP_ERR_CUDA, "qgmap_find_map: %s", cudaGetErrorString(e));
+    return QGMAP_OK;
+}
+
+// ---- one-call solver == gqmap_gpu_mixture(options,I1,I2) -----------------------------------------------------------------
+extern "C" int qgmap_solve(const qgmap_config *cfg, const double *I1, const double *I2, int Mo, int No, int its,
+                           const double *const *init, uint64_t seed, const double *tflow, const uint8_t *unknown,
+                           double *mu, double *sigma, double *alpha, double *AEPE, double *Energy, double *logP,
+                           int *its_done)
+{
+    qgmap_handle *nh = nullptr;
+    if (its < 1) QG_FAIL(nh, QGMAP_ERR_ARG, "qgmap_solve: its=%d", its);
+    qgmap_handle *h = nullptr;
+    int rc = qgmap_create(cfg, I1, I2, Mo, No, &h);
+    if (rc) return rc;
+    auto bail = [&](int code) { g_last_error = h->err; qgmap_destroy(h); return code; };
+    if (init) rc = qgmap_set_state(h, init[0], init[1], init[2], init[3], init[4], init[5], init[6], nullptr, cfg->temperature, 1);
+    else rc = qgmap_init_state(h, seed);
+    if (rc) return bail(rc);
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    for (int i = 0; i < its; ++i) {                                                  // :16
+        if (AEPE) AEPE[i] = nan;
+        if (Energy) Energy[i] = 0.0;
+        if (logP) logP[i] = nan;
+    }
+    if (tflow && (rc = upload_truth(h, tflow, unknown)) != QGMAP_OK) return bail(rc);
+    const int every = cfg->log_every > 0 ? cfg->log_every : 300;
+    int it = 1, stopped = 0;
+    long long launches = 0;
+    float ms = 0.f;
+    while (!stopped && it <= its) {
+        // run up to and including the next monitored iteration (:52: mod(it,300)==0 || it==1)
+        const int next_mon = (it == 1) ? 1 : ((it + every - 1) / every) * every;
+        const int n = std::min(next_mon, its) - it + 1;
+        int done = 0;
+        rc = qgmap_step(h, n, its, Energy ? Energy + (it - 1) : nullptr, nullptr, nullptr, &done, &stopped);
+        if (rc) return bail(rc);
+        launches += h->last_launches; ms += h->last_ms;
+        it += done;
+        const int last = it - 1;                                                      // last executed iteration
+        if (done > 0 && (last == 1 || last % every == 0)) {                           // :52-68
+            if ((rc = map_device(h)) != QGMAP_OK) return bail(rc);
+            if (tflow && AEPE && (rc = aepe_device(h, h->d_map, &AEPE[last - 1])) != QGMAP_OK) return bail(rc);
+            if (logP && (rc = logp_device(h, h->d_map, &logP[last - 1])) != QGMAP_OK) return bail(rc);
+            launches += 1 + (tflow && AEPE ? 1 : 0) + (logP ? 1 : 0);
+        }
+        if (done < n) break;
+    }
+    if (its_done) *its_done = it - 1;
+    const size_t n3 = (size_t)h->M * h->N * h->L;
+    std::vector<double> a(h->L);
+    rc = qgmap_get_state(h, mu, mu ? mu + n3 : nullptr, sigma, sigma ? sigma + n3 : nullptr, nullptr, nullptr, nullptr,
+                         a.data(), nullptr, nullptr);                                 // :183-185
+    if (rc) return bail(rc);
+    if (alpha) std::copy(a.begin(), a.end(), alpha);
+    g_solve_launches = launches; g_solve_ms = ms;
+    qgmap_destroy(h);
+    return QGMAP_OK;
+}
+
+void qgmap_launch_iteration(const qgmap_handle *h) { launch_iter(h, false); }
+void qgmap_launch_advance(const qgmap_handle *h) { qgmap_advance_kernel<<<1, 32, 0, h->stream>>>(h->params); }
+
+extern "C" int qgmap_last_solve_stats(long long *launches, float *kernel_ms)
+{
+    if (launches) *launches = g_solve_launches;
+    if (kernel_ms) *kernel_ms = g_solve_ms;
+    return QGMAP_OK;
+}

@@ -1,0 +1,68 @@
+// qgmap_internal.h -- private handle layout shared by the translation units of libqgmap.so.
+#pragma once
+#include "../../include/qgmap.h"
+#include "qgmap_device.cuh"
+#include <cuda_runtime.h>
+#include <string>
+
+struct QgMonParams;
+struct QgBand;
+
+struct qgmap_handle {
+    qgmap_config cfg{};
+    int Mo = 0, No = 0, M = 0, N = 0, L = 0, K = 0;
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // band geometry: rows [row_begin,row_end) owned; [g0,g1) stored; [out_r0,out_r1) updated
+    int row_begin = 0, row_end = 0, g0 = 0, g1 = 0, rows_local = 0, out_r0 = 0, out_r1 = 0;
+    int P = 0;
+    long long plane = 0;
+    float *I1f = nullptr, *VVf = nullptr;
+    double *I1d = nullptr, *VVd = nullptr;
+    int pitchI = 0, pitchV = 0;
+    float *buf[2] = {nullptr, nullptr};
+    float *dbg = nullptr;
+    QgCtrl *ctrl = nullptr, *ctrl_host = nullptr;
+    double *partials = nullptr;
+    double *hist[3] = {nullptr, nullptr, nullptr};
+    int hist_cap = 0;
+    double *stage = nullptr;
+    size_t stage_cap = 0;
+    double *mon_partials = nullptr, *d_map = nullptr, *d_tflow = nullptr;
+    unsigned char *d_unknown = nullptr;
+    bool has_unknown = false, has_state = false;
+    QgIterParams params{};
+    dim3 grid{};
+    cudaGraphExec_t graph = nullptr;
+    float last_ms = 0.f;
+    long long last_launches = 0;
+    int rank = 0, nranks = 1;
+    QgBand *band = nullptr;
+    std::string err;
+};
+
+// qgmap_map.cu (compiled with -fmad=false: fp64 monitoring arithmetic must not be contracted)
+void qgmap_launch_find_map_f32(const double *alpha, const float *mu_u, const float *sig_u, const float *mu_v,
+                               const float *sig_v, long long comp_stride, int M, int N, int L, int pitch, int row_off,
+                               double *map, long long total, cudaStream_t s);
+void qgmap_launch_find_map_f64(const double *alpha, const double *mu_u, const double *sig_u, const double *mu_v,
+                               const double *sig_v, long long comp_stride, int M, int N, int L, double *map,
+                               long long total, cudaStream_t s);
+struct QgMonArgs {
+    const double *I1; int pitchI; const double *VV; int pitchV;
+    int Mo, No, M, N, super; double lambdad, lambdas, epsn;
+};
+void qgmap_launch_logp(const QgMonArgs &q, const double *uv, double *partials, int nblk, cudaStream_t s);
+void qgmap_launch_aepe(const QgMonArgs &q, const double *map, const double *tflow, const unsigned char *unknown,
+                       double *partials, int nblk, cudaStream_t s);
+
+// qgmap_band.cu: row-band decomposition over NCCL
+void qgmap_band_release(qgmap_handle *h);
+int qgmap_band_refresh(qgmap_handle *h);                       // exchange halo rows of the current state
+int qgmap_band_iteration(qgmap_handle *h, long long *launches); // one iteration incl. all-reduce + halo exchange
+void qgmap_launch_iteration(const qgmap_handle *h);             // plain iteration kernel launch on h->stream
+void qgmap_launch_advance(const qgmap_handle *h);
+
+extern thread_local long long g_solve_launches;
+extern thread_local float g_solve_ms;

@@ -1,0 +1,277 @@
+// qgmap_iter.cuh -- the fused QGMAP iteration kernel (one launch == one pass of gqmap_gpu_mixture.m:27-50,69-75).
+//
+// One thread per (belief pixel, mixture component): node quadrature (:87-116), the pixel's down and right edge
+// quadratures for both flow layers (:118-146), gradient assembly with the neighbours' endpoint-2 contributions
+// (:36-40), ascent step + clamps (:41-46), and the block partial sums for Energy / d(alpha) / mean|grad|
+// (:36,:48,:69-70).  The last block to finish reduces the partials in a fixed order and advances the device-resident
+// control block (step counter, alpha softmax / projsplx update :50,:78-86, temperature anneal S:72, stop test :75).
+//
+// Tiling: a CTA is 32 lanes x (QG_TH+1) warps.  Warp 0 is the halo row above the tile and lane 0 the halo column left
+// of it: they evaluate only the edge whose endpoint-2 gradient an output pixel needs (Jacobi semantics: every gradient
+// uses the OLD state, written state goes to the other ping-pong buffer).  Down-edge endpoint-2 gradients travel through
+// shared memory to the warp below, right-edge ones through a warp shuffle to the next lane.  Output tile = 31 x QG_TH.
+#pragma once
+#include "qgmap_device.cuh"
+
+__device__ __forceinline__ float qg_clamp(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+__device__ __forceinline__ float qg_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// projsplx.m:15-32 on <= QG_LMAX doubles
+__device__ inline void qg_projsplx(const double *y, int m, double *x) {
+    double s[QG_LMAX];
+    for (int i = 0; i < m; ++i) s[i] = y[i];
+    for (int i = 0; i < m; ++i)
+        for (int j = i + 1; j < m; ++j)
+            if (s[j] > s[i]) { double t = s[i]; s[i] = s[j]; s[j] = t; }
+    bool bget = false;
+    double tmpsum = 0.0, tmax = 0.0;
+    for (int ii = 1; ii <= m - 1; ++ii) {
+        tmpsum += s[ii - 1];
+        tmax = (tmpsum - 1.0) / (double)ii;
+        if (tmax >= s[ii]) { bget = true; break; }
+    }
+    if (!bget) tmax = (tmpsum + s[m - 1] - 1.0) / (double)m;
+    for (int i = 0; i < m; ++i) x[i] = fmax(y[i] - tmax, 0.0);
+}
+
+// Control-block advance, executed by ONE thread once the global sums of this iteration are known.
+// sums[l*QG_NRED + {0:energy,1:dalpha,2:sum|G_muu|,3:sum|G_sigu|}].
+__device__ inline void qg_advance(const QgIterParams &p, QgCtrl *c, const double *sums)
+{
+    const int L = p.L, it = c->it;
+    double E = 0.0, sdm = 0.0, sds = 0.0, dalpha[QG_LMAX];
+    for (int l = 0; l < L; ++l) {
+        E += sums[l * QG_NRED + 0];
+        dalpha[l] = sums[l * QG_NRED + 1];
+        sdm += sums[l * QG_NRED + 2];
+        sds += sums[l * QG_NRED + 3];
+        c->dalpha[l] = dalpha[l];
+    }
+    const double cnt = (double)(p.M - 2) * (double)(p.N - 2) * (double)L;
+    const double ptdmu = sdm / cnt, ptdsig = sds / cnt;
+    p.hist_energy[it - 1] = E;                                                   // :48
+    p.hist_dmu[it - 1] = ptdmu;                                                  // :69-70
+    p.hist_dsig[it - 1] = ptdsig;
+    const double step = p.step0 / (1.0 + (double)it / p.step_tau);               // :27
+    if (it > p.alpha_start && L != 1) {                                          // :50
+        if (p.alpha_mode == 1) {                                                 // :49 (commented alternative)
+            double y[QG_LMAX];
+            for (int l = 0; l < L; ++l) y[l] = c->alpha[l] + dalpha[l] * step * p.alpha_scale;
+            qg_projsplx(y, L, c->alpha);
+        } else {                                                                 // updateAlpha :78-86
+            double dot = 0.0, se = 0.0;
+            for (int l = 0; l < L; ++l) dot += dalpha[l] * c->alpha[l];
+            for (int l = 0; l < L; ++l) {
+                double dw = c->alpha[l] * (dalpha[l] - dot);
+                c->w[l] = fmin(fmax(c->w[l] + dw * step * p.alpha_scale, -300.0), 300.0);
+            }
+            for (int l = 0; l < L; ++l) se += exp(c->w[l]);
+            for (int l = 0; l < L; ++l) c->alpha[l] = exp(c->w[l]) / se;
+        }
+    }
+    if (p.anneal_every > 0 && it % p.anneal_every == 0) c->T = fmax(c->T * p.drate, p.T_floor);   // S:72
+    c->it = it + 1;                                                              // :74
+    if (it + 1 > c->its || ptdmu < p.tor) c->stop = 1;                           // :75
+}
+
+template <int KT, bool SUPER, bool DUMP>
+__global__ void __launch_bounds__(QG_TW *(QG_TH + 1))
+qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
+{
+    QgCtrl *ctrl = p.ctrl;
+    if (!DUMP && ctrl->stop) return;
+    const int it = ctrl->it;
+    const float *__restrict__ in = p.buf[(it - 1) & 1];
+    float *__restrict__ out = p.buf[it & 1];
+
+    const int j = threadIdx.x, r = threadIdx.y;
+    const int l = blockIdx.z;
+    const int n = (int)blockIdx.x * (QG_TW - 1) + j;              // global column (lane 0 = halo column n0-1)
+    const int m = p.out_r0 + (int)blockIdx.y * QG_TH + r - 1;     // global row    (warp 0 = halo row m0-1)
+    const bool incol = (n >= 1) && (n <= p.N - 2);                // interior column
+    const bool inrow = (m >= p.out_r0) && (m < p.out_r1);         // row this handle updates (interior by construction)
+    const bool is_out = (r >= 1) && (j >= 1) && inrow && incol;
+    // halo warp: down edge of the row above the tile; halo lane: right edge of the column left of the tile
+    const bool need_down = is_out || ((r == 0) && (j >= 1) && incol && (m + 1 < p.out_r1));
+    const bool need_right = is_out || ((j == 0) && (r >= 1) && inrow && (n + 1 <= p.N - 2));
+    const bool active = need_down || need_right;
+
+    const float a = (float)ctrl->alpha[l];
+    const float T = (float)ctrl->T;
+    const float step = (float)(p.step0 / (1.0 + (double)it / p.step_tau));      // :27
+
+    const long long pl = p.plane;
+    const float *base = in + (long long)l * pl;
+    const long long idx = (long long)(m - p.g0) * p.P + n;
+    const long long fstr = (long long)p.L * pl;                                 // field stride
+
+    float muu = 0.f, muv = 0.f, sigu = 1.f, sigv = 1.f;
+    if (active) {
+        muu = __ldg(base + F_MUU * fstr + idx);  muv = __ldg(base + F_MUV * fstr + idx);
+        sigu = __ldg(base + F_SIGU * fstr + idx); sigv = __ldg(base + F_SIGV * fstr + idx);
+    }
+
+    QgGrad gdu = {}, gdv = {}, gru = {}, grv = {}, gn = {};
+    float rou0 = 0.f, rou1 = 0.f, rou2 = 0.f, rou3 = 0.f, pn = 0.f;
+
+    // ---- down edge (m,n)->(m+1,n), layers u and v  (:31-34, e=1) ------------------------------------------------
+    if (need_down) {
+        const long long idn = idx + p.P;
+        rou0 = __ldg(base + F_ROU0 * fstr + idx);
+        rou2 = __ldg(base + F_ROU2 * fstr + idx);
+        gdu = qg_edge<KT>(p.tab, p.K, a, muu, __ldg(base + F_MUU * fstr + idn), sigu, __ldg(base + F_SIGU * fstr + idn),
+                          rou0, p.lambdas, p.epsn, T);
+        gdv = qg_edge<KT>(p.tab, p.K, a, muv, __ldg(base + F_MUV * fstr + idn), sigv, __ldg(base + F_SIGV * fstr + idn),
+                          rou2, p.lambdas, p.epsn, T);
+    }
+    // ---- right edge (m,n)->(m,n+1)  (e=2) -----------------------------------------------------------------------
+    if (need_right) {
+        const long long irt = idx + 1;
+        rou1 = __ldg(base + F_ROU1 * fstr + idx);
+        rou3 = __ldg(base + F_ROU3 * fstr + idx);
+        gru = qg_edge<KT>(p.tab, p.K, a, muu, __ldg(base + F_MUU * fstr + irt), sigu, __ldg(base + F_SIGU * fstr + irt),
+                          rou1, p.lambdas, p.epsn, T);
+        grv = qg_edge<KT>(p.tab, p.K, a, muv, __ldg(base + F_MUV * fstr + irt), sigv, __ldg(base + F_SIGV * fstr + irt),
+                          rou3, p.lambdas, p.epsn, T);
+    }
+    // ---- node term (:29, :87-116) -------------------------------------------------------------------------------
+    if (is_out) {
+        pn = __ldg(base + F_PN * fstr + idx);
+        QgSpectral sp;
+        sp.set(pn);
+        QgMoments mo;
+        if (SUPER) {
+            float I1b[16];
+            const float *ip = p.I1 + (long long)(4 * m) * p.pitchI + 4 * n;
+#pragma unroll
+            for (int di = 0; di < 4; ++di) {
+                float4 v = __ldg(reinterpret_cast<const float4 *>(ip + (long long)di * p.pitchI));
+                I1b[di * 4 + 0] = v.x; I1b[di * 4 + 1] = v.y; I1b[di * 4 + 2] = v.z; I1b[di * 4 + 3] = v.w;
+            }
+            const int lastx = p.No - 2, lasty = p.Mo - 2, m4 = 4 * m, n4 = 4 * n;
+            mo = qg_quadrature<KT>(p.tab, p.K, muu, muv, sigu, sigv, sp, -p.lambdad, [&](float x1, float x2) {
+                return qg_super_sample(p.VV, p.pitchV, m4, n4, lastx, lasty, x1, x2, I1b, p.epsn);
+            });
+        } else {
+            const float I1v = __ldg(p.I1 + (long long)m * p.pitchI + n);
+            const int lastx = p.No - 2, lasty = p.Mo - 2;
+            mo = qg_quadrature<KT>(p.tab, p.K, muu, muv, sigu, sigv, sp, -p.lambdad, [&](float x1, float x2) {
+                return qg_node_sample(p.VV, p.pitchV, m, n, lastx, lasty, x1, x2, I1v, p.epsn);
+            });
+        }
+        gn = qg_epilogue(mo, sp, a, sigu, sigv, pn, -3.0f * T);
+    }
+
+    // ---- endpoint-2 exchange ------------------------------------------------------------------------------------
+    __shared__ float4 sh_dn[QG_TH + 1][QG_TW];
+    __shared__ double sh_red[QG_TH + 1][QG_NRED];
+    __shared__ int sh_last;
+    sh_dn[r][j] = make_float4(gdu.du2, gdu.do2, gdv.du2, gdv.do2);          // to pixel (m+1,n)
+    const float lf_du_u = __shfl_up_sync(0xffffffffu, gru.du2, 1);             // from pixel (m,n-1)
+    const float lf_do_u = __shfl_up_sync(0xffffffffu, gru.do2, 1);
+    const float lf_du_v = __shfl_up_sync(0xffffffffu, grv.du2, 1);
+    const float lf_do_v = __shfl_up_sync(0xffffffffu, grv.do2, 1);
+    __syncthreads();
+
+    float red[QG_NRED] = {0.f, 0.f, 0.f, 0.f};
+    if (is_out) {
+        const float4 up = sh_dn[r - 1][j];
+        // :37-40  node + sum_e d1 + shifted d2 (down edge of (m-1,n), right edge of (m,n-1))
+        const float G_muu = ((gn.du1 + (gdu.du1 + gru.du1)) + up.x) + lf_du_u;
+        const float G_sigu = ((gn.do1 + (gdu.do1 + gru.do1)) + up.y) + lf_do_u;
+        const float G_muv = ((gn.du2 + (gdv.du1 + grv.du1)) + up.z) + lf_du_v;
+        const float G_sigv = ((gn.do2 + (gdv.do1 + grv.do1)) + up.w) + lf_do_v;
+        const float e_px = gn.Ei + ((gdu.Ei + gru.Ei) + (gdv.Ei + grv.Ei));      // :48
+        const float da_px = gn.da + ((gdu.da + gru.da) + (gdv.da + grv.da));     // :36
+        red[0] = e_px; red[1] = da_px; red[2] = fabsf(G_muu); red[3] = fabsf(G_sigu);
+        if (DUMP) {
+            float *d = p.dbg + (long long)l * pl + idx;
+            d[0 * fstr] = G_muu; d[1 * fstr] = G_muv; d[2 * fstr] = G_sigu; d[3 * fstr] = G_sigv;
+            d[4 * fstr] = gn.dp; d[5 * fstr] = gdu.dp; d[6 * fstr] = gru.dp; d[7 * fstr] = gdv.dp; d[8 * fstr] = grv.dp;
+            d[9 * fstr] = e_px; d[10 * fstr] = da_px;
+        } else {
+            float *o = out + (long long)l * pl + idx;                            // :41-46
+            o[F_MUU * fstr] = qg_clamp(fmaf(G_muu, step, muu), p.minu, p.maxu);
+            o[F_MUV * fstr] = qg_clamp(fmaf(G_muv, step, muv), p.minv, p.maxv);
+            o[F_SIGU * fstr] = qg_clamp(fmaf(G_sigu, step, sigu), p.sig_min, p.sig_max);
+            o[F_SIGV * fstr] = qg_clamp(fmaf(G_sigv, step, sigv), p.sig_min, p.sig_max);
+            o[F_PN * fstr] = qg_clamp(fmaf(gn.dp, step, pn), -p.corr_tor, p.corr_tor);
+            o[F_ROU0 * fstr] = qg_clamp(fmaf(gdu.dp, step, rou0), -p.corr_tor, p.corr_tor);
+            o[F_ROU1 * fstr] = qg_clamp(fmaf(gru.dp, step, rou1), -p.corr_tor, p.corr_tor);
+            o[F_ROU2 * fstr] = qg_clamp(fmaf(gdv.dp, step, rou2), -p.corr_tor, p.corr_tor);
+            o[F_ROU3 * fstr] = qg_clamp(fmaf(grv.dp, step, rou3), -p.corr_tor, p.corr_tor);
+        }
+    }
+
+    // ---- block partial sums (fp32 within a warp, fp64 across warps and blocks) ------------------------------------
+#pragma unroll
+    for (int k = 0; k < QG_NRED; ++k) {
+        float v = qg_warp_sum(red[k]);
+        if (j == 0) sh_red[r][k] = (double)v;
+    }
+    __syncthreads();
+    const int tid = r * QG_TW + j;
+    const unsigned int nblk_l = gridDim.x * gridDim.y;
+    const unsigned int blk = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (tid < QG_NRED) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 1; w <= QG_TH; ++w) s += sh_red[w][tid];
+        p.partials[(size_t)blk * QG_NRED + tid] = s;
+    }
+    if (DUMP) return;
+
+    // ---- last block: deterministic global reduction + control advance --------------------------------------------
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int t = atomicAdd(&ctrl->ticket, 1u);
+        sh_last = (t == nblk_l * gridDim.z - 1);
+    }
+    __syncthreads();
+    if (!sh_last) return;
+    __threadfence();
+    __shared__ double sh_sum[QG_LMAX * QG_NRED];
+    const int nthr = QG_TW * (QG_TH + 1), warp = tid >> 5, lane = tid & 31, nwarp = nthr / 32;
+    for (int ll = 0; ll < p.L; ++ll) {
+        double acc[QG_NRED] = {0.0, 0.0, 0.0, 0.0};
+        const double *pp = p.partials + (size_t)ll * nblk_l * QG_NRED;
+        for (unsigned int b = tid; b < nblk_l; b += nthr) {
+#pragma unroll
+            for (int k = 0; k < QG_NRED; ++k) acc[k] += __ldcg(pp + (size_t)b * QG_NRED + k);
+        }
+#pragma unroll
+        for (int k = 0; k < QG_NRED; ++k) {
+            double v = acc[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) sh_red[warp][k] = v;
+        }
+        __syncthreads();
+        if (tid < QG_NRED) {
+            double s = 0.0;
+            for (int w = 0; w < nwarp; ++w) s += sh_red[w][tid];
+            sh_sum[ll * QG_NRED + tid] = s;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        ctrl->ticket = 0;
+        if (p.band) {
+            for (int k = 0; k < p.L * QG_NRED; ++k) ctrl->sums[k] = sh_sum[k];   // all-reduced across ranks, then
+        } else {                                                               // qgmap_advance_kernel runs qg_advance
+            qg_advance(p, ctrl, sh_sum);
+        }
+    }
+}
+
+// Band mode: after the NCCL all-reduce of ctrl->sums, one thread advances the control block.
+__global__ void qgmap_advance_kernel(const __grid_constant__ QgIterParams p)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0 && !p.ctrl->stop) qg_advance(p, p.ctrl, p.ctrl->sums);
+}

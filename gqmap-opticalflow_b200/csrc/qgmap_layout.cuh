@@ -1,0 +1,71 @@
+// qgmap_layout.cuh -- layout conversion at the C-ABI boundary (MATLAB column-major fp64 <-> private row-major planes)
+// and the device-side getVV.
+#pragma once
+#include <cuda_runtime.h>
+
+// ---- layout conversion kernels (MATLAB column-major fp64 at the boundary <-> private row-major planes) ------------
+// src: column-major fp64 [rows x cols x planes]; dst: row-major T planes with pitch; copies rows [r0,r1) to local rows.
+template <typename T>
+__global__ void qgmap_import_kernel(const double *__restrict__ src, int rows, int cols, int planes, T *__restrict__ dst,
+                                    int pitch, long long plane_stride, int r0, int r1, int g0)
+{
+    __shared__ double tile[32][33];
+    const int pz = blockIdx.z;
+    const int rb = r0 + blockIdx.y * 32, cb = blockIdx.x * 32;
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {           // coalesced along rows (column-major source)
+        int rr = rb + threadIdx.x, cc = cb + k;
+        if (rr < r1 && cc < cols) tile[k][threadIdx.x] = src[rr + (long long)rows * cc + (long long)rows * cols * pz];
+    }
+    __syncthreads();
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {           // coalesced along cols (row-major destination)
+        int rr = rb + k, cc = cb + threadIdx.x;
+        if (rr < r1 && cc < cols) dst[(long long)pz * plane_stride + (long long)(rr - g0) * pitch + cc] = (T)tile[threadIdx.x][k];
+    }
+}
+
+template <typename T>
+__global__ void qgmap_export_kernel(const T *__restrict__ src, int pitch, long long plane_stride, int g0, int r0, int r1,
+                                    double *__restrict__ dst, int rows, int cols)
+{
+    __shared__ double tile[32][33];
+    const int pz = blockIdx.z;
+    const int rb = r0 + blockIdx.y * 32, cb = blockIdx.x * 32;
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        int rr = rb + k, cc = cb + threadIdx.x;
+        if (rr < r1 && cc < cols) tile[k][threadIdx.x] = (double)src[(long long)pz * plane_stride + (long long)(rr - g0) * pitch + cc];
+    }
+    __syncthreads();
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+        int rr = rb + threadIdx.x, cc = cb + k;
+        if (rr < r1 && cc < cols) dst[rr + (long long)rows * cc + (long long)rows * cols * pz] = tile[threadIdx.x][k];
+    }
+}
+
+// getVV (gqmap_gpu_mixture.m:191-208) on the device, fp64 row-major: first pass copies the interior and extrapolates
+// the top/bottom rows of every column (corners still zero), second pass the left/right columns of every row.
+static __global__ void qgmap_vv_rows_kernel(const double *__restrict__ I2 /* col-major Mo x No */, int Mo, int No,
+                                     double *__restrict__ VV, int pitchV)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;            // padded column 0..No+1
+    if (c > No + 1) return;
+    auto in = [&](int r) -> double {                                // padded row r in 1..Mo, padded col c
+        return (c >= 1 && c <= No) ? I2[(r - 1) + (long long)Mo * (c - 1)] : 0.0;
+    };
+    for (int r = 1; r <= Mo; ++r) VV[(long long)r * pitchV + c] = in(r);
+    VV[c] = (3.0 * in(1) - 3.0 * in(2)) + in(3);                                          // :201
+    VV[(long long)(Mo + 1) * pitchV + c] = (3.0 * in(Mo) - 3.0 * in(Mo - 1)) + in(Mo - 2); // :202
+}
+static __global__ void qgmap_vv_cols_kernel(int Mo, int No, double *__restrict__ VV, int pitchV)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;            // padded row 0..Mo+1
+    if (r > Mo + 1) return;
+    double *row = VV + (long long)r * pitchV;
+    row[0] = (3.0 * row[1] - 3.0 * row[2]) + row[3];                                      // :205
+    row[No + 1] = (3.0 * row[No] - 3.0 * row[No - 1]) + row[No - 2];                      // :206
+}
+template <typename T>
+__global__ void qgmap_cast_kernel(const double *__restrict__ src, T *__restrict__ dst, long long n)
+{
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+        dst[t] = (T)src[t];
+}
