@@ -52,6 +52,10 @@ SIGNATURES = {
     "qgmap_get_state": (C.c_int, [C.c_void_p] + [_DP] * 8 + [_DP, _IP]),
     "qgmap_init_state": (C.c_int, [C.c_void_p, C.c_uint64]),
     "qgmap_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _DP, _DP, _DP, _IP, _IP]),
+    "qgmap_step_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "qgmap_step_end": (C.c_int, [C.c_void_p, _DP, _DP, _DP, _IP, _IP]),
+    "qgmap_batch_step": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_longlong)]),
+    "qgmap_fp32_peak": (C.c_int, [C.c_int, _DP]),
     "qgmap_last_step_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "qgmap_last_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong)]),
     "qgmap_get_map": (C.c_int, [C.c_void_p, _DP]),

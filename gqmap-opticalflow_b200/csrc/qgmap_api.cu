@@ -104,6 +104,8 @@ static void free_handle(qgmap_handle *h)
     if (h->graph) cudaGraphExecDestroy(h->graph);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->evb0) cudaEventDestroy(h->evb0);
+    if (h->evb1) cudaEventDestroy(h->evb1);
     void *ptrs[] = {h->I1f, h->VVf, h->I1d, h->VVd, h->buf[0], h->buf[1], h->dbg, h->ctrl, h->partials, h->hist[0],
                     h->hist[1], h->hist[2], h->stage, h->mon_partials, h->d_map, h->d_tflow, h->d_unknown};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -124,7 +126,7 @@ static int ensure_stage(qgmap_handle *h, size_t doubles)
 static int ensure_hist(qgmap_handle *h, int its)
 {
     if (its <= h->hist_cap) return QGMAP_OK;
-    int cap = std::max(its, 1024);
+    int cap = (int)std::min<long long>(std::max<long long>({(long long)its, 2LL * h->hist_cap, 1024LL}), 1LL << 30);
     for (int k = 0; k < 3; ++k) {
         double *n = nullptr;
         QG_CUDA(h, cudaMalloc(&n, (size_t)cap * sizeof(double)));
@@ -396,16 +398,18 @@ static int build_graph(qgmap_handle *h)
     return QGMAP_OK;
 }
 
-extern "C" int qgmap_step(qgmap_handle *h, int n, int its, double *energy, double *ptdmu, double *ptdsigma,
-                          int *n_done, int *stopped)
+// enqueue up to n iterations on the handle's stream; returns without waiting
+extern "C" int qgmap_step_begin(qgmap_handle *h, int n, int its)
 {
     if (!h) return QGMAP_ERR_ARG;
     if (n < 0 || its < 1) QG_FAIL(h, QGMAP_ERR_ARG, "qgmap_step: n=%d its=%d", n, its);
     if (!h->has_state) QG_FAIL(h, QGMAP_ERR_STATE, "qgmap_step before qgmap_set_state/qgmap_init_state");
+    if (h->pending) QG_FAIL(h, QGMAP_ERR_STATE, "qgmap_step_begin: previous step not ended");
     QG_CUDA(h, cudaSetDevice(h->device));
-    int rc = ensure_hist(h, its);
+    // history is indexed by iteration: room for what can actually run now (its may be "unbounded")
+    int rc = ensure_hist(h, (int)std::min<long long>((long long)its, (long long)h->ctrl_host->it - 1 + n));
     if (rc) return rc;
-    const int it0 = h->ctrl_host->it;
+    h->it0 = h->ctrl_host->it;
     if (h->ctrl_host->its != its) {
         h->ctrl_host->its = its;
         // the reference tests `it > its` after incrementing: a run resumed past its stops after one more iteration
@@ -423,17 +427,121 @@ extern "C" int qgmap_step(qgmap_handle *h, int n, int its, double *energy, doubl
     }
     QG_CUDA(h, cudaGetLastError());
     QG_CUDA(h, cudaEventRecord(h->ev1, h->stream));
-    if ((rc = sync_ctrl(h)) != QGMAP_OK) return rc;
-    QG_CUDA(h, cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    QG_CUDA(h, cudaMemcpyAsync(h->ctrl_host, h->ctrl, sizeof(QgCtrl), cudaMemcpyDeviceToHost, h->stream));
     h->last_launches = launches;
-    const int done = h->ctrl_host->it - it0;
+    h->pending = true;
+    return QGMAP_OK;
+}
+
+// wait for the iterations enqueued by qgmap_step_begin and fetch their per-iteration history
+extern "C" int qgmap_step_end(qgmap_handle *h, double *energy, double *ptdmu, double *ptdsigma, int *n_done, int *stopped)
+{
+    if (!h) return QGMAP_ERR_ARG;
+    if (!h->pending) QG_FAIL(h, QGMAP_ERR_STATE, "qgmap_step_end without qgmap_step_begin");
+    QG_CUDA(h, cudaSetDevice(h->device));
+    h->pending = false;
+    QG_CUDA(h, cudaStreamSynchronize(h->stream));
+    QG_CUDA(h, cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    const int done = h->ctrl_host->it - h->it0;
     if (n_done) *n_done = done;
     if (stopped) *stopped = h->ctrl_host->stop;
     double *dst[3] = {energy, ptdmu, ptdsigma};
+    bool any = false;
     for (int k = 0; k < 3; ++k)
-        if (dst[k] && done > 0)
-            QG_CUDA(h, cudaMemcpyAsync(dst[k], h->hist[k] + (it0 - 1), (size_t)done * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    QG_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (dst[k] && done > 0) {
+            QG_CUDA(h, cudaMemcpyAsync(dst[k], h->hist[k] + (h->it0 - 1), (size_t)done * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            any = true;
+        }
+    if (any) QG_CUDA(h, cudaStreamSynchronize(h->stream));
+    return QGMAP_OK;
+}
+
+extern "C" int qgmap_step(qgmap_handle *h, int n, int its, double *energy, double *ptdmu, double *ptdsigma,
+                          int *n_done, int *stopped)
+{
+    int rc = qgmap_step_begin(h, n, its);
+    if (rc) return rc;
+    return qgmap_step_end(h, energy, ptdmu, ptdsigma, n_done, stopped);
+}
+
+// Independent frame pairs (one handle each, all on the same device): run n iterations on every handle concurrently, each
+// on its own stream, and time the whole batch on the device (event on the first handle's stream before, after all).
+extern "C" int qgmap_batch_step(qgmap_handle **hs, int nh, int n, int its, float *device_ms, long long *launches)
+{
+    qgmap_handle *nh0 = nullptr;
+    if (!hs || nh < 1) QG_FAIL(nh0, QGMAP_ERR_ARG, "qgmap_batch_step: empty batch");
+    for (int i = 0; i < nh; ++i)
+        if (!hs[i] || hs[i]->device != hs[0]->device) QG_FAIL(nh0, QGMAP_ERR_ARG, "qgmap_batch_step: handles must share a device");
+    qgmap_handle *h0 = hs[0];
+    QG_CUDA(h0, cudaSetDevice(h0->device));
+    if (!h0->evb0) { QG_CUDA(h0, cudaEventCreate(&h0->evb0)); QG_CUDA(h0, cudaEventCreate(&h0->evb1)); }
+    for (int i = 0; i < nh; ++i) QG_CUDA(hs[i], cudaStreamSynchronize(hs[i]->stream));
+    QG_CUDA(h0, cudaEventRecord(h0->evb0, h0->stream));
+    for (int i = 1; i < nh; ++i) QG_CUDA(hs[i], cudaStreamWaitEvent(hs[i]->stream, h0->evb0, 0));
+    int rc;
+    long long nl = 0;
+    for (int i = 0; i < nh; ++i) {
+        if ((rc = qgmap_step_begin(hs[i], n, its)) != QGMAP_OK) { g_last_error = hs[i]->err; return rc; }
+        nl += hs[i]->last_launches;
+    }
+    for (int i = 1; i < nh; ++i) QG_CUDA(h0, cudaStreamWaitEvent(h0->stream, hs[i]->ev1, 0));
+    QG_CUDA(h0, cudaEventRecord(h0->evb1, h0->stream));
+    for (int i = 0; i < nh; ++i)
+        if ((rc = qgmap_step_end(hs[i], nullptr, nullptr, nullptr, nullptr, nullptr)) != QGMAP_OK) { g_last_error = hs[i]->err; return rc; }
+    QG_CUDA(h0, cudaEventSynchronize(h0->evb1));
+    float ms = 0.f;
+    QG_CUDA(h0, cudaEventElapsedTime(&ms, h0->evb0, h0->evb1));
+    if (device_ms) *device_ms = ms;
+    if (launches) *launches = nl;
+    return QGMAP_OK;
+}
+
+// Measured FP32 FMA throughput of the device (register-resident FFMA chains): the roofline denominator bench.py reports
+// beside the nominal 148 SM x 128 lanes x 2 x clock figure.
+__global__ void qgmap_ffma_probe_kernel(float *out, int iters)
+{
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float b = 1.0000001f, c = 1e-7f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+            a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+extern "C" int qgmap_fp32_peak(int device, double *tflops)
+{
+    qgmap_handle *nh = nullptr;
+    if (!tflops) return QGMAP_ERR_ARG;
+    int dev;
+    int rc = device_check(nh, device, &dev);
+    if (rc) return rc;
+    cudaDeviceProp prop;
+    QG_CUDA(nh, cudaGetDeviceProperties(&prop, dev));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    float *d = nullptr;
+    QG_CUDA(nh, cudaMalloc(&d, (size_t)blocks * threads * sizeof(float)));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(e0);
+        qgmap_ffma_probe_kernel<<<blocks, threads>>>(d, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double tf = 2.0 * 128.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaError_t e = cudaGetLastError();
+    cudaFree(d);
+    if (e != cudaSuccess) QG_FAIL(nh, QGMAP_ERR_CUDA, "qgmap_fp32_peak: %s", cudaGetErrorString(e));
+    *tflops = best;
     return QGMAP_OK;
 }
 

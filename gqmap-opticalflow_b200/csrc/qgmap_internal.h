@@ -13,7 +13,9 @@ struct qgmap_handle {
     int Mo = 0, No = 0, M = 0, N = 0, L = 0, K = 0;
     int device = -1;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evb0 = nullptr, evb1 = nullptr;
+    bool pending = false;      // qgmap_step_begin without qgmap_step_end
+    int it0 = 0;               // iteration counter when the pending step began
     // band geometry: rows [row_begin,row_end) owned; [g0,g1) stored; [out_r0,out_r1) updated
     int row_begin = 0, row_end = 0, g0 = 0, g1 = 0, rows_local = 0, out_r0 = 0, out_r1 = 0;
     int P = 0;

@@ -264,3 +264,19 @@ class Solver:
         out = {n: np.zeros((self.M, self.N, self.L, 2, 2) if n == "drou" else (self.M, self.N, self.L), order="F") for n in names}
         check(lib.qgmap_debug_gradients(self._h, *(dptr(out[n]) for n in names)), self._h)
         return out
+
+
+def batch_step(solvers, n, its=2 ** 30):
+    """Run n iterations on every Solver of a same-device batch concurrently; returns (device_ms, kernel launches)."""
+    arr = (C.c_void_p * len(solvers))(*[s._h for s in solvers])
+    ms = C.c_float(0)
+    nl = C.c_longlong(0)
+    check(lib.qgmap_batch_step(arr, len(solvers), int(n), int(its), C.byref(ms), C.byref(nl)))
+    return ms.value, nl.value
+
+
+def fp32_peak(device=-1):
+    """Measured FP32 FMA throughput of the device in TFLOP/s (roofline denominator)."""
+    v = C.c_double(0)
+    check(lib.qgmap_fp32_peak(int(device), C.byref(v)))
+    return v.value

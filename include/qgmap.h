@@ -100,6 +100,15 @@ int qgmap_init_state(qgmap_handle *h, uint64_t seed);
  * of each executed iteration.  *n_done iterations executed, *stopped = 1 if the break condition fired. */
 int qgmap_step(qgmap_handle *h, int n, int its, double *energy, double *ptdmu, double *ptdsigma,
                int *n_done, int *stopped);
+/* The same split in two so that independent handles overlap: begin enqueues (no wait), end waits and fetches. */
+int qgmap_step_begin(qgmap_handle *h, int n, int its);
+int qgmap_step_end(qgmap_handle *h, double *energy, double *ptdmu, double *ptdsigma, int *n_done, int *stopped);
+/* Independent frame pairs (BASELINE config "batch of frame pairs"): n iterations on each of nh handles of ONE device,
+ * concurrently on their own streams; *device_ms = device time of the whole batch (CUDA events), *launches = kernels. */
+int qgmap_batch_step(qgmap_handle **hs, int nh, int n, int its, float *device_ms, long long *launches);
+/* Measured FP32 FMA throughput (TFLOP/s) of `device`: the roofline denominator for the FP32-bound iteration kernel. */
+int qgmap_fp32_peak(int device, double *tflops);
+
 /* Device time (CUDA events on the handle's stream) of the kernels launched by the last qgmap_step, in ms. */
 int qgmap_last_step_ms(const qgmap_handle *h, float *ms);
 /* Number of kernels the last qgmap_step / qgmap_solve launched (for the bench's gpu_launches claim). */
