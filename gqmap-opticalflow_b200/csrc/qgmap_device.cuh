@@ -41,7 +41,8 @@ struct QgCtrl {
 
 struct QgIterParams {
     const float *I1;  int pitchI;      // Mo x No row-major
-    const float *VV;  int pitchV;      // (Mo+2) x (No+2) row-major padded second frame (getVV)
+    const float4 *VV4; int pitchV;     // padded second frame (getVV), packed: VV4[y*pitchV + x] = VV(y, x..x+3), so the 4 taps of
+                                       // one bicubic row are ONE 16-byte load (4 LDG.128 per sample instead of 16 LDG.32)
     float *buf[2];                     // ping-pong state: 9 fields x L planes of rows_local x P floats
     long long plane;                   // floats per plane (rows_local * P)
     int P;                             // row pitch of state planes (floats)
@@ -133,66 +134,73 @@ __device__ __forceinline__ void qg_cubic_w(float s, float &w0, float &w1, float 
     w3 = s2 * tm;                                    // (s-1)s^2
 }
 
+// floor(x) as int + exact fraction without the XU pipe (FRND/F2I are quarter-rate): add 1.5*2^23 so the integer part lands
+// in the mantissa, read it back as an integer, fix up round-to-nearest -> floor.  Valid for |x| < 2^22.
+__device__ __forceinline__ int qg_floor_split(float x, float &frac) {
+    const float magic = 12582912.0f;
+    const float t = x + magic;
+    int i = __float_as_int(t) - 0x4B400000;
+    float r = t - magic;
+    if (r > x) { r -= 1.0f; i -= 1; }
+    frac = x - r;                                    // exact in fp32
+    return i;
+}
+
 // floor/fraction split + reference clamping (:157-162) for one axis.  pix = 0-based pixel index, x = displacement,
 // last = size-2 (largest valid 0-based cell origin).  Returns cell origin; frac in [0,1].
 __device__ __forceinline__ int qg_cell(int pix, float x, int last, float &frac) {
-    float fl = floorf(x);
-    frac = x - fl;                                   // exact in fp32
-    int c = pix + (int)fl;
+    int c = pix + qg_floor_split(x, frac);
     if (c < 0) { c = 0; frac = 0.0f; }
     else if (c > last) { c = last; frac = 1.0f; }
     return c;
 }
 
+__device__ __forceinline__ float qg_dot4(const float4 v, float a0, float a1, float a2, float a3) {
+    return fmaf(v.w, a3, fmaf(v.z, a2, fmaf(v.y, a1, v.x * a0)));
+}
+
 // sqrt(eps + (I1 - bicubic(VV))^2) at displacement (x1 horizontal, x2 vertical) from pixel (m,n) (0-based).
 // node_pot = -lambdad * this  (gqmap_gpu_mixture.m:156-179).
-__device__ __forceinline__ float qg_node_sample(const float *__restrict__ VV, int pitchV, int m, int n, int lastx,
+__device__ __forceinline__ float qg_node_sample(const float4 *__restrict__ VV4, int pitchV, int m, int n, int lastx,
                                                 int lasty, float x1, float x2, float I1v, float epsn)
 {
     float so, to;
-    int ix = qg_cell(n, x1, lastx, so);
-    int iy = qg_cell(m, x2, lasty, to);
+    const int ix = qg_cell(n, x1, lastx, so);
+    const int iy = qg_cell(m, x2, lasty, to);
+    const float4 *r0 = VV4 + (long long)iy * pitchV + ix;    // padded coords: taps rows iy..iy+3, cols ix..ix+3
+    const float4 v0 = __ldg(r0), v1 = __ldg(r0 + pitchV), v2 = __ldg(r0 + 2 * pitchV), v3 = __ldg(r0 + 3 * pitchV);
     float a0, a1, a2, a3, b0, b1, b2, b3;
     qg_cubic_w(so, a0, a1, a2, a3);
     qg_cubic_w(to, b0, b1, b2, b3);
-    const float *r0 = VV + (long long)iy * pitchV + ix;      // padded coords: taps rows iy..iy+3, cols ix..ix+3
-    const float *r1 = r0 + pitchV, *r2 = r1 + pitchV, *r3 = r2 + pitchV;
-    float h0 = __ldg(r0) * a0, h1 = __ldg(r1) * a0, h2 = __ldg(r2) * a0, h3 = __ldg(r3) * a0;
-    h0 = fmaf(__ldg(r0 + 1), a1, h0); h1 = fmaf(__ldg(r1 + 1), a1, h1);
-    h2 = fmaf(__ldg(r2 + 1), a1, h2); h3 = fmaf(__ldg(r3 + 1), a1, h3);
-    h0 = fmaf(__ldg(r0 + 2), a2, h0); h1 = fmaf(__ldg(r1 + 2), a2, h1);
-    h2 = fmaf(__ldg(r2 + 2), a2, h2); h3 = fmaf(__ldg(r3 + 2), a2, h3);
-    h0 = fmaf(__ldg(r0 + 3), a3, h0); h1 = fmaf(__ldg(r1 + 3), a3, h1);
-    h2 = fmaf(__ldg(r2 + 3), a3, h2); h3 = fmaf(__ldg(r3 + 3), a3, h3);
-    float v = fmaf(h3, b3, fmaf(h2, b2, fmaf(h1, b1, h0 * b0)));
-    float d = fmaf(-0.25f, v, I1v);
+    const float h0 = qg_dot4(v0, a0, a1, a2, a3), h1 = qg_dot4(v1, a0, a1, a2, a3);
+    const float h2 = qg_dot4(v2, a0, a1, a2, a3), h3 = qg_dot4(v3, a0, a1, a2, a3);
+    const float v = fmaf(h3, b3, fmaf(h2, b2, fmaf(h1, b1, h0 * b0)));
+    const float d = fmaf(-0.25f, v, I1v);
     return qg_sqrt(fmaf(d, d, epsn));
 }
 
 // Super-pixel node sample: sum over the block's 4x4 pixels (gqmap_gpuSuper_mix_entropy.m:99-104), block origin
 // pixel (m4,n4) 0-based.  When no pixel of the block is clamped all 16 samples share one set of bicubic weights and
 // a 7x7 footprint (49 loads, separable 112+64 FMAs instead of 16 x (16 loads + 20 FMAs)).
-__device__ __forceinline__ float qg_super_sample(const float *__restrict__ VV, int pitchV, int m4, int n4, int lastx,
+__device__ __forceinline__ float qg_super_sample(const float4 *__restrict__ VV4, int pitchV, int m4, int n4, int lastx,
                                                  int lasty, float x1, float x2, const float (&I1b)[16], float epsn)
 {
-    float fl1 = floorf(x1), fl2 = floorf(x2);
-    int ix = n4 + (int)fl1, iy = m4 + (int)fl2;
+    float so, to;
+    const int ix = n4 + qg_floor_split(x1, so), iy = m4 + qg_floor_split(x2, to);
     float acc = 0.0f;
     if (ix >= 0 && ix + 3 <= lastx && iy >= 0 && iy + 3 <= lasty) {
-        float so = x1 - fl1, to = x2 - fl2;
         float a0, a1, a2, a3, b[4];
         qg_cubic_w(so, a0, a1, a2, a3);
         qg_cubic_w(to, b[0], b[1], b[2], b[3]);
         float o[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) o[i] = 0.0f;
-        const float *rp = VV + (long long)iy * pitchV + ix;
+        const float4 *rp = VV4 + (long long)iy * pitchV + ix;
 #pragma unroll
         for (int row = 0; row < 7; ++row) {
-            float v[7];
-#pragma unroll
-            for (int c = 0; c < 7; ++c) v[c] = __ldg(rp + c);
+            const float4 lo = __ldg(rp), hi = __ldg(rp + 3);          // cols ix..ix+3 and ix+3..ix+6
             rp += pitchV;
+            const float v[7] = {lo.x, lo.y, lo.z, lo.w, hi.y, hi.z, hi.w};
 #pragma unroll
             for (int dj = 0; dj < 4; ++dj) {
                 float h = fmaf(v[dj + 3], a3, fmaf(v[dj + 2], a2, fmaf(v[dj + 1], a1, v[dj] * a0)));
@@ -213,7 +221,7 @@ __device__ __forceinline__ float qg_super_sample(const float *__restrict__ VV, i
         for (int di = 0; di < 4; ++di)
 #pragma unroll 1
             for (int dj = 0; dj < 4; ++dj)
-                acc += qg_node_sample(VV, pitchV, m4 + di, n4 + dj, lastx, lasty, x1, x2, I1b[di * 4 + dj], epsn);
+                acc += qg_node_sample(VV4, pitchV, m4 + di, n4 + dj, lastx, lasty, x1, x2, I1b[di * 4 + dj], epsn);
     }
     return acc;
 }

@@ -20,7 +20,9 @@ struct qgmap_handle {
     int row_begin = 0, row_end = 0, g0 = 0, g1 = 0, rows_local = 0, out_r0 = 0, out_r1 = 0;
     int P = 0;
     long long plane = 0;
-    float *I1f = nullptr, *VVf = nullptr;
+    float *I1f = nullptr;
+    float4 *VVf = nullptr;     // packed padded second frame (see QgIterParams::VV4)
+    int pitch4 = 0;
     double *I1d = nullptr, *VVd = nullptr;
     int pitchI = 0, pitchV = 0;
     float *buf[2] = {nullptr, nullptr};

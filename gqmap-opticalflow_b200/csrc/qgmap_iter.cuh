@@ -80,7 +80,7 @@ __device__ inline void qg_advance(const QgIterParams &p, QgCtrl *c, const double
 }
 
 template <int KT, bool SUPER, bool DUMP>
-__global__ void __launch_bounds__(QG_TW *(QG_TH + 1))
+__global__ void __launch_bounds__(QG_TW *(QG_TH + 1), SUPER ? 2 : 3)
 qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
 {
     QgCtrl *ctrl = p.ctrl;
@@ -116,8 +116,8 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
         sigu = __ldg(base + F_SIGU * fstr + idx); sigv = __ldg(base + F_SIGV * fstr + idx);
     }
 
-    QgGrad gdu = {}, gdv = {}, gru = {}, grv = {}, gn = {};
-    float rou0 = 0.f, rou1 = 0.f, rou2 = 0.f, rou3 = 0.f, pn = 0.f;
+    QgGrad gdu = {}, gdv = {}, gru = {}, grv = {};
+    float rou0 = 0.f, rou1 = 0.f, rou2 = 0.f, rou3 = 0.f;
 
     // ---- down edge (m,n)->(m+1,n), layers u and v  (:31-34, e=1) ------------------------------------------------
     if (need_down) {
@@ -139,9 +139,42 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
         grv = qg_edge<KT>(p.tab, p.K, a, muv, __ldg(base + F_MUV * fstr + irt), sigv, __ldg(base + F_SIGV * fstr + irt),
                           rou3, p.lambdas, p.epsn, T);
     }
-    // ---- node term (:29, :87-116) -------------------------------------------------------------------------------
+    // ---- endpoint-2 exchange (before the node term: the warps of a CTA then never wait for each other again until the
+    //      final block reduction, and the cheap halo warp does not stall the barrier) ---------------------------------
+    __shared__ float4 sh_dn[QG_TH + 1][QG_TW];
+    __shared__ double sh_red[QG_TH + 1][QG_NRED];
+    __shared__ int sh_last;
+    sh_dn[r][j] = make_float4(gdu.du2, gdu.do2, gdv.du2, gdv.do2);          // to pixel (m+1,n)
+    const float lf_du_u = __shfl_up_sync(0xffffffffu, gru.du2, 1);             // from pixel (m,n-1)
+    const float lf_do_u = __shfl_up_sync(0xffffffffu, gru.do2, 1);
+    const float lf_du_v = __shfl_up_sync(0xffffffffu, grv.du2, 1);
+    const float lf_do_v = __shfl_up_sync(0xffffffffu, grv.do2, 1);
+    __syncthreads();
+
+    float red[QG_NRED] = {0.f, 0.f, 0.f, 0.f};
     if (is_out) {
-        pn = __ldg(base + F_PN * fstr + idx);
+        // :37-40 edge part of the assembled gradients: sum_e d1 + shifted d2 (down edge of (m-1,n), right edge of (m,n-1)).
+        // Folded into 6 scalars now so that little stays live across the node quadrature.
+        const float4 up = sh_dn[r - 1][j];
+        const float E_muu = ((gdu.du1 + gru.du1) + up.x) + lf_du_u;
+        const float E_sigu = ((gdu.do1 + gru.do1) + up.y) + lf_do_u;
+        const float E_muv = ((gdv.du1 + grv.du1) + up.z) + lf_du_v;
+        const float E_sigv = ((gdv.do1 + grv.do1) + up.w) + lf_do_v;
+        const float E_e = (gdu.Ei + gru.Ei) + (gdv.Ei + grv.Ei);                 // :48 edge part
+        const float E_a = (gdu.da + gru.da) + (gdv.da + grv.da);                 // :36 edge part
+        float *o = out + (long long)l * pl + idx;
+        float *d = DUMP ? p.dbg + (long long)l * pl + idx : nullptr;
+        if (DUMP) {
+            d[5 * fstr] = gdu.dp; d[6 * fstr] = gru.dp; d[7 * fstr] = gdv.dp; d[8 * fstr] = grv.dp;
+        } else {                                                                 // :45
+            o[F_ROU0 * fstr] = qg_clamp(fmaf(gdu.dp, step, rou0), -p.corr_tor, p.corr_tor);
+            o[F_ROU1 * fstr] = qg_clamp(fmaf(gru.dp, step, rou1), -p.corr_tor, p.corr_tor);
+            o[F_ROU2 * fstr] = qg_clamp(fmaf(gdv.dp, step, rou2), -p.corr_tor, p.corr_tor);
+            o[F_ROU3 * fstr] = qg_clamp(fmaf(grv.dp, step, rou3), -p.corr_tor, p.corr_tor);
+        }
+
+        // ---- node term (:29, :87-116) ---------------------------------------------------------------------------
+        const float pn = __ldg(base + F_PN * fstr + idx);
         QgSpectral sp;
         sp.set(pn);
         QgMoments mo;
@@ -155,56 +188,31 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
             }
             const int lastx = p.No - 2, lasty = p.Mo - 2, m4 = 4 * m, n4 = 4 * n;
             mo = qg_quadrature<KT>(p.tab, p.K, muu, muv, sigu, sigv, sp, -p.lambdad, [&](float x1, float x2) {
-                return qg_super_sample(p.VV, p.pitchV, m4, n4, lastx, lasty, x1, x2, I1b, p.epsn);
+                return qg_super_sample(p.VV4, p.pitchV, m4, n4, lastx, lasty, x1, x2, I1b, p.epsn);
             });
         } else {
             const float I1v = __ldg(p.I1 + (long long)m * p.pitchI + n);
             const int lastx = p.No - 2, lasty = p.Mo - 2;
             mo = qg_quadrature<KT>(p.tab, p.K, muu, muv, sigu, sigv, sp, -p.lambdad, [&](float x1, float x2) {
-                return qg_node_sample(p.VV, p.pitchV, m, n, lastx, lasty, x1, x2, I1v, p.epsn);
+                return qg_node_sample(p.VV4, p.pitchV, m, n, lastx, lasty, x1, x2, I1v, p.epsn);
             });
         }
-        gn = qg_epilogue(mo, sp, a, sigu, sigv, pn, -3.0f * T);
-    }
+        const QgGrad gn = qg_epilogue(mo, sp, a, sigu, sigv, pn, -3.0f * T);
 
-    // ---- endpoint-2 exchange ------------------------------------------------------------------------------------
-    __shared__ float4 sh_dn[QG_TH + 1][QG_TW];
-    __shared__ double sh_red[QG_TH + 1][QG_NRED];
-    __shared__ int sh_last;
-    sh_dn[r][j] = make_float4(gdu.du2, gdu.do2, gdv.du2, gdv.do2);          // to pixel (m+1,n)
-    const float lf_du_u = __shfl_up_sync(0xffffffffu, gru.du2, 1);             // from pixel (m,n-1)
-    const float lf_do_u = __shfl_up_sync(0xffffffffu, gru.do2, 1);
-    const float lf_du_v = __shfl_up_sync(0xffffffffu, grv.du2, 1);
-    const float lf_do_v = __shfl_up_sync(0xffffffffu, grv.do2, 1);
-    __syncthreads();
-
-    float red[QG_NRED] = {0.f, 0.f, 0.f, 0.f};
-    if (is_out) {
-        const float4 up = sh_dn[r - 1][j];
-        // :37-40  node + sum_e d1 + shifted d2 (down edge of (m-1,n), right edge of (m,n-1))
-        const float G_muu = ((gn.du1 + (gdu.du1 + gru.du1)) + up.x) + lf_du_u;
-        const float G_sigu = ((gn.do1 + (gdu.do1 + gru.do1)) + up.y) + lf_do_u;
-        const float G_muv = ((gn.du2 + (gdv.du1 + grv.du1)) + up.z) + lf_du_v;
-        const float G_sigv = ((gn.do2 + (gdv.do1 + grv.do1)) + up.w) + lf_do_v;
-        const float e_px = gn.Ei + ((gdu.Ei + gru.Ei) + (gdv.Ei + grv.Ei));      // :48
-        const float da_px = gn.da + ((gdu.da + gru.da) + (gdv.da + grv.da));     // :36
+        const float G_muu = gn.du1 + E_muu, G_sigu = gn.do1 + E_sigu;
+        const float G_muv = gn.du2 + E_muv, G_sigv = gn.do2 + E_sigv;
+        const float e_px = gn.Ei + E_e;                                          // :48
+        const float da_px = gn.da + E_a;                                         // :36
         red[0] = e_px; red[1] = da_px; red[2] = fabsf(G_muu); red[3] = fabsf(G_sigu);
         if (DUMP) {
-            float *d = p.dbg + (long long)l * pl + idx;
             d[0 * fstr] = G_muu; d[1 * fstr] = G_muv; d[2 * fstr] = G_sigu; d[3 * fstr] = G_sigv;
-            d[4 * fstr] = gn.dp; d[5 * fstr] = gdu.dp; d[6 * fstr] = gru.dp; d[7 * fstr] = gdv.dp; d[8 * fstr] = grv.dp;
-            d[9 * fstr] = e_px; d[10 * fstr] = da_px;
-        } else {
-            float *o = out + (long long)l * pl + idx;                            // :41-46
+            d[4 * fstr] = gn.dp; d[9 * fstr] = e_px; d[10 * fstr] = da_px;
+        } else {                                                                 // :41-44, :46
             o[F_MUU * fstr] = qg_clamp(fmaf(G_muu, step, muu), p.minu, p.maxu);
             o[F_MUV * fstr] = qg_clamp(fmaf(G_muv, step, muv), p.minv, p.maxv);
             o[F_SIGU * fstr] = qg_clamp(fmaf(G_sigu, step, sigu), p.sig_min, p.sig_max);
             o[F_SIGV * fstr] = qg_clamp(fmaf(G_sigv, step, sigv), p.sig_min, p.sig_max);
             o[F_PN * fstr] = qg_clamp(fmaf(gn.dp, step, pn), -p.corr_tor, p.corr_tor);
-            o[F_ROU0 * fstr] = qg_clamp(fmaf(gdu.dp, step, rou0), -p.corr_tor, p.corr_tor);
-            o[F_ROU1 * fstr] = qg_clamp(fmaf(gru.dp, step, rou1), -p.corr_tor, p.corr_tor);
-            o[F_ROU2 * fstr] = qg_clamp(fmaf(gdv.dp, step, rou2), -p.corr_tor, p.corr_tor);
-            o[F_ROU3 * fstr] = qg_clamp(fmaf(grv.dp, step, rou3), -p.corr_tor, p.corr_tor);
         }
     }
 

@@ -69,3 +69,13 @@ __global__ void qgmap_cast_kernel(const double *__restrict__ src, T *__restrict_
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
         dst[t] = (T)src[t];
 }
+
+// Packed second frame for the iteration kernel: VV4[y*pitch4 + x] = (VV(y,x), VV(y,x+1), VV(y,x+2), VV(y,x+3)), x <= width-4.
+static __global__ void qgmap_pack4_kernel(const double *__restrict__ VV, int pitchV, int rows, int width, float4 *__restrict__ out, int pitch4)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= pitch4 || y >= rows) return;
+    const double *r = VV + (long long)y * pitchV;
+    auto g = [&](int c) -> float { return c < width ? (float)r[c] : 0.0f; };
+    out[(long long)y * pitch4 + x] = make_float4(g(x), g(x + 1), g(x + 2), g(x + 3));
+}
