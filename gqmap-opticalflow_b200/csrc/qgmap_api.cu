@@ -193,7 +193,7 @@ extern "C" int qgmap_create(const qgmap_config *cfg, const double *I1, const dou
     QG_CUDA_C(cudaMalloc(&h->VVd, nV * sizeof(double)));
     QG_CUDA_C(cudaMalloc(&h->I1f, nI * sizeof(float)));
     h->pitch4 = (No + 3) / 4 * 4;
-    QG_CUDA_C(cudaMalloc(&h->VVf, (size_t)(Mo + 2) * h->pitch4 * sizeof(float4)));
+    QG_CUDA_C(cudaMalloc(&h->VVf, (size_t)(Mo + 2) * h->pitch4 * sizeof(QgTap8)));       // entry rows 0..Mo+1
     QG_CUDA_C(cudaMemsetAsync(h->I1d, 0, nI * sizeof(double), h->stream));
     QG_CUDA_C(cudaMemsetAsync(h->VVd, 0, nV * sizeof(double), h->stream));
     {
@@ -208,7 +208,8 @@ extern "C" int qgmap_create(const qgmap_config *cfg, const double *I1, const dou
         qgmap_vv_rows_kernel<<<(No + 2 + 127) / 128, 128, 0, h->stream>>>(h->stage, Mo, No, h->VVd, h->pitchV);
         qgmap_vv_cols_kernel<<<(Mo + 2 + 127) / 128, 128, 0, h->stream>>>(Mo, No, h->VVd, h->pitchV);
         qgmap_cast_kernel<float><<<256, 256, 0, h->stream>>>(h->I1d, h->I1f, (long long)nI);
-        qgmap_pack4_kernel<<<dim3((h->pitch4 + 127) / 128, Mo + 2), 128, 0, h->stream>>>(h->VVd, h->pitchV, Mo + 2, No + 2, h->VVf, h->pitch4);
+        qgmap_pack8_kernel<<<dim3((h->pitch4 + 127) / 128, Mo + 2), 128, 0, h->stream>>>(h->VVd, h->pitchV, Mo + 2, No + 2,
+                                                                                      reinterpret_cast<float4 *>(h->VVf), h->pitch4, Mo + 2);
         QG_CUDA_C(cudaGetLastError());
     }
 
@@ -232,7 +233,7 @@ extern "C" int qgmap_create(const qgmap_config *cfg, const double *I1, const dou
         p.tab.X[k] = (float)X[k]; p.tab.W[k] = (float)W[k];
         p.tab.WX[k] = (float)(W[k] * X[k]); p.tab.WXX[k] = (float)(W[k] * X[k] * X[k]);
     }
-    p.I1 = h->I1f; p.pitchI = h->pitchI; p.VV4 = h->VVf; p.pitchV = h->pitch4;
+    p.I1 = h->I1f; p.pitchI = h->pitchI; p.VV8 = h->VVf; p.pitchV = h->pitch4;
     p.buf[0] = h->buf[0]; p.buf[1] = h->buf[1];
     p.plane = h->plane; p.P = h->P; p.M = M; p.N = N; p.L = h->L; p.Mo = Mo; p.No = No;
     p.g0 = h->g0; p.out_r0 = h->out_r0; p.out_r1 = h->out_r1; p.K = h->K; p.band = 0;

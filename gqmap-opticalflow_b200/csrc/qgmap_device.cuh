@@ -18,6 +18,17 @@
 #define QG_TH 8             // output rows per tile (+1 halo row of threads)
 #define QG_NRED 4           // block-reduced scalars: energy, dalpha, sum|G_muu|, sum|G_sigu|
 
+struct __align__(32) QgTap8 { float4 r0, r1; };   // two consecutive image rows x four consecutive columns
+
+// sm_100 256-bit read-only global load (SASS LDG.E.ENL2.256.CONSTANT)
+__device__ __forceinline__ QgTap8 qg_ld256(const QgTap8 *p) {
+    QgTap8 v;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(v.r0.x), "=f"(v.r0.y), "=f"(v.r0.z), "=f"(v.r0.w), "=f"(v.r1.x), "=f"(v.r1.y), "=f"(v.r1.z), "=f"(v.r1.w)
+        : "l"(p));
+    return v;
+}
+
 struct QgTables {           // GaussHermite_2 nodes/weights, premultiplied (gqmap_gpu_mixture.m:8-10)
     float X[QG_KMAX];       // X(c)
     float W[QG_KMAX];       // W(c)
@@ -41,8 +52,9 @@ struct QgCtrl {
 
 struct QgIterParams {
     const float *I1;  int pitchI;      // Mo x No row-major
-    const float4 *VV4; int pitchV;     // padded second frame (getVV), packed: VV4[y*pitchV + x] = VV(y, x..x+3), so the 4 taps of
-                                       // one bicubic row are ONE 16-byte load (4 LDG.128 per sample instead of 16 LDG.32)
+    const QgTap8 *VV8; int pitchV;     // padded second frame (getVV), packed for the gather: VV8[y*pitchV + x] holds
+                                       // VV(y, x..x+3) and VV(y+1, x..x+3) in one 32-byte sector, so the 16 taps of a bicubic
+                                       // sample are TWO 256-bit loads (LDG.E.256), each lane touching exactly one sector
     float *buf[2];                     // ping-pong state: 9 fields x L planes of rows_local x P floats
     long long plane;                   // floats per plane (rows_local * P)
     int P;                             // row pitch of state planes (floats)
@@ -126,24 +138,23 @@ __device__ __forceinline__ QgGrad qg_epilogue(const QgMoments &m, const QgSpectr
 
 // ---- bicubic taps ---------------------------------------------------------------------------------------------
 // 2 x Keys(a=-0.5) weights, gqmap_gpu_mixture.m:164,170,172,174 (the /4 of :176 is applied by the caller).
+// w0 = -s(s-1)^2, w3 = s^2(s-1); the other two follow from the partition of unity (sum = 2) and the first moment
+// (-w0 + w2 + 2 w3 = 2s): 8 FMA-pipe operations per axis.
 __device__ __forceinline__ void qg_cubic_w(float s, float &w0, float &w1, float &w2, float &w3) {
-    float s2 = s * s, tm = s - 1.0f, st = s * tm;
-    w0 = -st * tm;                                   // ((2-s)s-1)s = -s(s-1)^2
-    w1 = fmaf(fmaf(3.0f, s, -5.0f), s2, 2.0f);       // (3s-5)s^2+2
-    w2 = fmaf(fmaf(-3.0f, s, 4.0f), s, 1.0f) * s;    // ((4-3s)s+1)s
-    w3 = s2 * tm;                                    // (s-1)s^2
+    const float tm = s - 1.0f, st = s * tm;
+    w0 = -st * tm;
+    w3 = st * s;
+    w2 = fmaf(-2.0f, w3, fmaf(2.0f, s, w0));
+    w1 = (2.0f - st) - w2;
 }
 
-// floor(x) as int + exact fraction without the XU pipe (FRND/F2I are quarter-rate): add 1.5*2^23 so the integer part lands
-// in the mantissa, read it back as an integer, fix up round-to-nearest -> floor.  Valid for |x| < 2^22.
+// floor(x) as int + exact fraction without the XU pipe (FRND/F2I are quarter-rate): add 1.5*2^23 rounding towards -inf,
+// so floor(x) lands in the mantissa; read it back as an integer.  Valid for |x| < 2^22.
 __device__ __forceinline__ int qg_floor_split(float x, float &frac) {
     const float magic = 12582912.0f;
-    const float t = x + magic;
-    int i = __float_as_int(t) - 0x4B400000;
-    float r = t - magic;
-    if (r > x) { r -= 1.0f; i -= 1; }
-    frac = x - r;                                    // exact in fp32
-    return i;
+    const float t = __fadd_rd(x, magic);
+    frac = x - (t - magic);                          // both subtractions exact in fp32
+    return __float_as_int(t) - 0x4B400000;
 }
 
 // floor/fraction split + reference clamping (:157-162) for one axis.  pix = 0-based pixel index, x = displacement,
@@ -161,19 +172,19 @@ __device__ __forceinline__ float qg_dot4(const float4 v, float a0, float a1, flo
 
 // sqrt(eps + (I1 - bicubic(VV))^2) at displacement (x1 horizontal, x2 vertical) from pixel (m,n) (0-based).
 // node_pot = -lambdad * this  (gqmap_gpu_mixture.m:156-179).
-__device__ __forceinline__ float qg_node_sample(const float4 *__restrict__ VV4, int pitchV, int m, int n, int lastx,
+__device__ __forceinline__ float qg_node_sample(const QgTap8 *__restrict__ VV8, int pitchV, int m, int n, int lastx,
                                                 int lasty, float x1, float x2, float I1v, float epsn)
 {
     float so, to;
     const int ix = qg_cell(n, x1, lastx, so);
     const int iy = qg_cell(m, x2, lasty, to);
-    const float4 *r0 = VV4 + (long long)iy * pitchV + ix;    // padded coords: taps rows iy..iy+3, cols ix..ix+3
-    const float4 v0 = __ldg(r0), v1 = __ldg(r0 + pitchV), v2 = __ldg(r0 + 2 * pitchV), v3 = __ldg(r0 + 3 * pitchV);
+    const QgTap8 *r0 = VV8 + (long long)iy * pitchV + ix;    // padded coords: taps rows iy..iy+3, cols ix..ix+3
+    const QgTap8 v01 = qg_ld256(r0), v23 = qg_ld256(r0 + 2 * pitchV);
     float a0, a1, a2, a3, b0, b1, b2, b3;
     qg_cubic_w(so, a0, a1, a2, a3);
     qg_cubic_w(to, b0, b1, b2, b3);
-    const float h0 = qg_dot4(v0, a0, a1, a2, a3), h1 = qg_dot4(v1, a0, a1, a2, a3);
-    const float h2 = qg_dot4(v2, a0, a1, a2, a3), h3 = qg_dot4(v3, a0, a1, a2, a3);
+    const float h0 = qg_dot4(v01.r0, a0, a1, a2, a3), h1 = qg_dot4(v01.r1, a0, a1, a2, a3);
+    const float h2 = qg_dot4(v23.r0, a0, a1, a2, a3), h3 = qg_dot4(v23.r1, a0, a1, a2, a3);
     const float v = fmaf(h3, b3, fmaf(h2, b2, fmaf(h1, b1, h0 * b0)));
     const float d = fmaf(-0.25f, v, I1v);
     return qg_sqrt(fmaf(d, d, epsn));
@@ -182,7 +193,7 @@ __device__ __forceinline__ float qg_node_sample(const float4 *__restrict__ VV4, 
 // Super-pixel node sample: sum over the block's 4x4 pixels (gqmap_gpuSuper_mix_entropy.m:99-104), block origin
 // pixel (m4,n4) 0-based.  When no pixel of the block is clamped all 16 samples share one set of bicubic weights and
 // a 7x7 footprint (49 loads, separable 112+64 FMAs instead of 16 x (16 loads + 20 FMAs)).
-__device__ __forceinline__ float qg_super_sample(const float4 *__restrict__ VV4, int pitchV, int m4, int n4, int lastx,
+__device__ __forceinline__ float qg_super_sample(const QgTap8 *__restrict__ VV8, int pitchV, int m4, int n4, int lastx,
                                                  int lasty, float x1, float x2, const float (&I1b)[16], float epsn)
 {
     float so, to;
@@ -195,19 +206,26 @@ __device__ __forceinline__ float qg_super_sample(const float4 *__restrict__ VV4,
         float o[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) o[i] = 0.0f;
-        const float4 *rp = VV4 + (long long)iy * pitchV + ix;
+        const QgTap8 *rp = VV8 + (long long)iy * pitchV + ix;
 #pragma unroll
-        for (int row = 0; row < 7; ++row) {
-            const float4 lo = __ldg(rp), hi = __ldg(rp + 3);          // cols ix..ix+3 and ix+3..ix+6
-            rp += pitchV;
-            const float v[7] = {lo.x, lo.y, lo.z, lo.w, hi.y, hi.z, hi.w};
+        for (int rr = 0; rr < 4; ++rr) {                                  // window rows 2rr, 2rr+1 (row 7 is loaded, unused)
+            const QgTap8 lo = qg_ld256(rp), hi = qg_ld256(rp + 3);        // cols ix..ix+3 and ix+3..ix+6
+            rp += 2 * pitchV;
 #pragma unroll
-            for (int dj = 0; dj < 4; ++dj) {
-                float h = fmaf(v[dj + 3], a3, fmaf(v[dj + 2], a2, fmaf(v[dj + 1], a1, v[dj] * a0)));
+            for (int half = 0; half < 2; ++half) {
+                const int row = 2 * rr + half;
+                if (row < 7) {
+                    const float4 l4 = half ? lo.r1 : lo.r0, h4 = half ? hi.r1 : hi.r0;
+                    const float v[7] = {l4.x, l4.y, l4.z, l4.w, h4.y, h4.z, h4.w};
 #pragma unroll
-                for (int di = 0; di < 4; ++di) {
-                    int r = row - di;                       // tap index of this window row for output row di
-                    if (r >= 0 && r < 4) o[di * 4 + dj] = fmaf(h, b[r], o[di * 4 + dj]);
+                    for (int dj = 0; dj < 4; ++dj) {
+                        float h = fmaf(v[dj + 3], a3, fmaf(v[dj + 2], a2, fmaf(v[dj + 1], a1, v[dj] * a0)));
+#pragma unroll
+                        for (int di = 0; di < 4; ++di) {
+                            int r = row - di;                       // tap index of this window row for output row di
+                            if (r >= 0 && r < 4) o[di * 4 + dj] = fmaf(h, b[r], o[di * 4 + dj]);
+                        }
+                    }
                 }
             }
         }
@@ -221,7 +239,7 @@ __device__ __forceinline__ float qg_super_sample(const float4 *__restrict__ VV4,
         for (int di = 0; di < 4; ++di)
 #pragma unroll 1
             for (int dj = 0; dj < 4; ++dj)
-                acc += qg_node_sample(VV4, pitchV, m4 + di, n4 + dj, lastx, lasty, x1, x2, I1b[di * 4 + dj], epsn);
+                acc += qg_node_sample(VV8, pitchV, m4 + di, n4 + dj, lastx, lasty, x1, x2, I1b[di * 4 + dj], epsn);
     }
     return acc;
 }

@@ -21,7 +21,7 @@ struct qgmap_handle {
     int P = 0;
     long long plane = 0;
     float *I1f = nullptr;
-    float4 *VVf = nullptr;     // packed padded second frame (see QgIterParams::VV4)
+    QgTap8 *VVf = nullptr;     // packed padded second frame (see QgIterParams::VV8)
     int pitch4 = 0;
     double *I1d = nullptr, *VVd = nullptr;
     int pitchI = 0, pitchV = 0;

@@ -188,13 +188,13 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
             }
             const int lastx = p.No - 2, lasty = p.Mo - 2, m4 = 4 * m, n4 = 4 * n;
             mo = qg_quadrature<KT>(p.tab, p.K, muu, muv, sigu, sigv, sp, -p.lambdad, [&](float x1, float x2) {
-                return qg_super_sample(p.VV4, p.pitchV, m4, n4, lastx, lasty, x1, x2, I1b, p.epsn);
+                return qg_super_sample(p.VV8, p.pitchV, m4, n4, lastx, lasty, x1, x2, I1b, p.epsn);
             });
         } else {
             const float I1v = __ldg(p.I1 + (long long)m * p.pitchI + n);
             const int lastx = p.No - 2, lasty = p.Mo - 2;
             mo = qg_quadrature<KT>(p.tab, p.K, muu, muv, sigu, sigv, sp, -p.lambdad, [&](float x1, float x2) {
-                return qg_node_sample(p.VV4, p.pitchV, m, n, lastx, lasty, x1, x2, I1v, p.epsn);
+                return qg_node_sample(p.VV8, p.pitchV, m, n, lastx, lasty, x1, x2, I1v, p.epsn);
             });
         }
         const QgGrad gn = qg_epilogue(mo, sp, a, sigu, sigv, pn, -3.0f * T);

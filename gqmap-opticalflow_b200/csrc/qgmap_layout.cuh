@@ -70,12 +70,15 @@ __global__ void qgmap_cast_kernel(const double *__restrict__ src, T *__restrict_
         dst[t] = (T)src[t];
 }
 
-// Packed second frame for the iteration kernel: VV4[y*pitch4 + x] = (VV(y,x), VV(y,x+1), VV(y,x+2), VV(y,x+3)), x <= width-4.
-static __global__ void qgmap_pack4_kernel(const double *__restrict__ VV, int pitchV, int rows, int width, float4 *__restrict__ out, int pitch4)
+// Packed second frame for the iteration kernel: out[y*pitch8 + x] = { VV(y, x..x+3), VV(y+1, x..x+3) } (zero beyond the
+// padded image), y = 0..rows-1 entries.
+static __global__ void qgmap_pack8_kernel(const double *__restrict__ VV, int pitchV, int rows_src, int width, float4 *__restrict__ out,
+                                          int pitch8, int rows_out)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= pitch4 || y >= rows) return;
-    const double *r = VV + (long long)y * pitchV;
-    auto g = [&](int c) -> float { return c < width ? (float)r[c] : 0.0f; };
-    out[(long long)y * pitch4 + x] = make_float4(g(x), g(x + 1), g(x + 2), g(x + 3));
+    if (x >= pitch8 || y >= rows_out) return;
+    auto g = [&](int r, int c) -> float { return (r < rows_src && c < width) ? (float)VV[(long long)r * pitchV + c] : 0.0f; };
+    float4 *o = out + 2 * ((long long)y * pitch8 + x);
+    o[0] = make_float4(g(y, x), g(y, x + 1), g(y, x + 2), g(y, x + 3));
+    o[1] = make_float4(g(y + 1, x), g(y + 1, x + 1), g(y + 1, x + 2), g(y + 1, x + 3));
 }
