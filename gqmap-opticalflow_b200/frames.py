@@ -77,16 +77,20 @@ def _bicubic(V, yq, xq):
 def synthetic_pair(M, N, seed=1234):
     """Synthetic frame pair of SURVEY.md section 8d: I1 = Gaussian-blurred (sigma 1.5) uniform noise scaled to [0,255];
     ground-truth flow u = 3 sin(2 pi row/M) + 1 (horizontal), v = 2 cos(2 pi col/N) (vertical); I2 = I1 warped so that
-    I2(row+v, col+u) ~ I1(row,col) (backward warp of I1 by the negated flow, bicubic).
+    I2(row+v, col+u) = I1(row,col) (bicubic resampling of I1 at the inverse flow, found by fixed-point iteration).
     Returns I1, I2 (M x N float64, 0..255), flow (M x N x 2), and (minu,maxu,minv,maxv)."""
     rng = np.random.default_rng(seed)
     a = _gauss_blur(rng.random((M, N)), 1.5)
     I1 = (a - a.min()) / (a.max() - a.min()) * 255.0
     rows = np.arange(M, dtype=np.float64).reshape(M, 1)
     cols = np.arange(N, dtype=np.float64).reshape(1, N)
-    u = 3.0 * np.sin(2 * np.pi * rows / M) + 1.0 + 0.0 * cols
-    v = 2.0 * np.cos(2 * np.pi * cols / N) + 0.0 * rows
-    # I2(y,x) = I1(y - v, x - u) (first-order inverse of the forward flow; smooth flow so the error is sub-pixel)
-    I2 = _bicubic(I1, rows - v, cols - u)
+    fu = lambda r, c: 3.0 * np.sin(2 * np.pi * r / M) + 1.0 + 0.0 * c
+    fv = lambda r, c: 2.0 * np.cos(2 * np.pi * c / N) + 0.0 * r
+    u, v = fu(rows, cols), fv(rows, cols)
+    # I2(q) = I1(p) with p + flow(p) = q: invert the (smooth, contractive) flow by fixed-point iteration
+    pr, pc = rows - v, cols - u
+    for _ in range(30):
+        pr, pc = rows - fv(pr, pc), cols - fu(pr, pc)
+    I2 = _bicubic(I1, pr, pc)
     flow = np.asfortranarray(np.stack([u, v], axis=2))
     return np.asfortranarray(I1), np.asfortranarray(I2), flow, (float(u.min()), float(u.max()), float(v.min()), float(v.max()))

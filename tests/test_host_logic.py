@@ -1,0 +1,96 @@
+"""Host-side logic of the product that needs no GPU, checked against the oracle / known answers."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+
+def test_gauss_hermite_product_vs_oracle(pkg, O):
+    for n in range(1, 33):
+        x, w = pkg.GaussHermite_2(n)
+        assert x.shape == (n, 1) and w.shape == (n, 1)                 # column vectors, as GaussHermite_2.m:30-32
+        if n >= 2:
+            xo, wo = O.gauss_hermite(n)
+            assert np.abs(x.ravel() - xo).max() < 1e-13 and np.abs(w.ravel() - wo).max() < 1e-14
+        assert abs(w.sum() - np.sqrt(np.pi)) < 1e-13
+        assert np.array_equal(x.ravel(), -x.ravel()[::-1])             # exactly symmetric tables
+    with pytest.raises(pkg.QgmapError):
+        pkg.GaussHermite_2(33)
+
+
+def test_projsplx_product_vs_oracle(pkg, O):
+    rng = np.random.default_rng(0)
+    for m in (1, 2, 3, 5, 10):
+        for _ in range(40):
+            y = rng.normal(0, 1.5, m)
+            assert np.allclose(pkg.projsplx(y), O.projsplx(y), atol=1e-15)
+
+
+def test_flow_to_color_product_vs_oracle(pkg, O):
+    rng = np.random.default_rng(1)
+    flow = rng.normal(0, 3, (33, 47, 2))
+    flow[rng.random((33, 47)) < 0.05] = 1e10
+    flow[5, 5] = (0.0, 0.0)
+    for mf in (None, 4.0):
+        a = pkg.flowToColor_mex(flow, mf)
+        b = O.flow_to_color(flow, -1.0 if mf is None else mf)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2:6] == b[2:6] and np.array_equal(a[6], b[6])
+    assert a[0].dtype == np.uint8 and a[0].shape == (33, 47, 3) and a[6].dtype == bool
+
+
+def test_read_flow_file(pkg, tmp_path):
+    h, w = 5, 7
+    u = np.arange(h * w, dtype=np.float32).reshape(h, w)
+    v = -u
+    inter = np.stack([u, v], axis=2).reshape(h, w * 2)
+    p = tmp_path / "t.flo"
+    with open(p, "wb") as f:
+        f.write(struct.pack("<f", 202021.25) + struct.pack("<ii", w, h) + inter.tobytes())
+    img = pkg.readFlowFile(str(p))
+    assert img.shape == (h, w, 2) and np.array_equal(img[:, :, 0], u) and np.array_equal(img[:, :, 1], v)
+    with pytest.raises(ValueError):
+        pkg.readFlowFile(str(tmp_path / "t.txt"))                      # readFlowFile.m:47-49
+    bad = tmp_path / "bad.flo"
+    bad.write_bytes(struct.pack("<f", 1.0) + struct.pack("<ii", w, h))
+    with pytest.raises(ValueError):
+        pkg.readFlowFile(str(bad))                                     # wrong tag, readFlowFile.m:62-64
+
+
+def test_rgb2gray_matlab_coefficients(pkg):
+    rgb = np.array([[[255, 0, 0], [0, 255, 0], [0, 0, 255], [255, 255, 255], [10, 20, 30]]], dtype=np.uint8)
+    assert pkg.rgb2gray(rgb).tolist() == [[76, 150, 29, 255, 18]]      # MATLAB rgb2gray on uint8
+
+
+def test_synthetic_pair_deterministic_and_consistent(pkg):
+    a = pkg.synthetic_pair(48, 64, seed=5)
+    b = pkg.synthetic_pair(48, 64, seed=5)
+    assert all(np.array_equal(x, y) for x, y in zip(a[:3], b[:3])) and a[3] == b[3]
+    I1, I2, flow, (minu, maxu, minv, maxv) = a
+    assert I1.min() == 0.0 and I1.max() == 255.0 and I1.flags.f_contiguous
+    assert abs(maxu - 4.0) < 0.02 and abs(minu + 2.0) < 0.02 and abs(maxv - 2.0) < 1e-12
+    # brightness constancy holds along the flow: I2(row+v, col+u) ~ I1(row, col) in the interior
+    from importlib import import_module
+    fr = import_module("gqmap-opticalflow_b200.frames")
+    rows = np.arange(48.0).reshape(48, 1); cols = np.arange(64.0).reshape(1, 64)
+    warped = fr._bicubic(I2, rows + flow[:, :, 1], cols + flow[:, :, 0])
+    assert np.abs(warped - I1)[8:-8, 8:-8].mean() < 2.0
+
+
+def test_make_config_maps_options(pkg):
+    o = dict(K=9, L=3, temperature=0.2, drate=0.75, epsn=1e-6, lambdad=1, lambdas=16, minu=-2, maxu=3, minv=-1, maxv=1,
+             alpha_mode="projsplx", sigma_max=17.0, alpha_start=700)
+    c = pkg.make_config(o, 1)
+    assert (c.K, c.L, c.temperature, c.drate, c.lambdas, c.minu, c.maxu, c.alpha_mode, c.sigma_max, c.alpha_start) == \
+           (9, 3, 0.2, 0.75, 16.0, -2.0, 3.0, 1, 17.0, 700)
+    assert c.anneal_every == 500 and c.step0 == 0.001                  # super-pixel constants kept
+    with pytest.raises(ValueError):
+        pkg.make_config(dict(o, alpha_mode="simplex"), 0)
+
+
+def test_mex_gateways_compile_against_stub():
+    mexdir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gqmap-opticalflow_b200", "mex")
+    import subprocess
+    subprocess.check_call(["make", "-C", mexdir, "-B"], stdout=subprocess.DEVNULL)
+    for f in ("gqmap_mex.o", "get_map_mex.o", "flowToColor_mex.o"):
+        assert os.path.exists(os.path.join(mexdir, f))
