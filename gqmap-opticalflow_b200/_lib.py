@@ -71,6 +71,14 @@ SIGNATURES = {
     "qgmap_debug_gradients": (C.c_int, [C.c_void_p] + [_DP] * 8),
     "qgmap_band_unique_id": (C.c_int, [C.c_void_p]),
     "qgmap_band_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "qgmap_group_create": (C.c_int, [C.POINTER(QgmapConfig), _DP, _DP, C.c_int, C.c_int, C.c_int, _IP, C.POINTER(C.c_void_p)]),
+    "qgmap_group_destroy": (C.c_int, [C.c_void_p]),
+    "qgmap_group_dims": (C.c_int, [C.c_void_p, _IP, _IP, _IP, _IP]),
+    "qgmap_group_set_state": (C.c_int, [C.c_void_p] + [_DP] * 8 + [C.c_double, C.c_int]),
+    "qgmap_group_init_state": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "qgmap_group_get_state": (C.c_int, [C.c_void_p] + [_DP] * 8 + [_DP, _IP]),
+    "qgmap_group_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _DP, _DP, _DP, _IP, _IP]),
+    "qgmap_group_last_step_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "qgmap_last_error": (C.c_char_p, [C.c_void_p]),
     "qgmap_status_string": (C.c_char_p, [C.c_int]),
     "qgmap_version": (C.c_int, []),

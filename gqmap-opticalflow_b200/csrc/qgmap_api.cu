@@ -16,6 +16,13 @@
 static thread_local std::string g_last_error;
 thread_local long long g_solve_launches = 0;
 thread_local float g_solve_ms = 0.f;
+void qgmap_set_last_error(const char *msg) { g_last_error = msg ? msg : ""; }
+
+// Band mode (multi-process): after the NCCL all-reduce of ctrl->sums one thread advances the control block.
+__global__ void qgmap_advance_kernel(const __grid_constant__ QgIterParams p)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0 && !p.ctrl->stop) qg_advance(p, p.ctrl, p.ctrl->sums);
+}
 
 #define QG_FAIL(h, code, ...)                                                        \
     do {                                                                             \
@@ -400,8 +407,8 @@ static int build_graph(qgmap_handle *h)
     return QGMAP_OK;
 }
 
-// enqueue up to n iterations on the handle's stream; returns without waiting
-extern "C" int qgmap_step_begin(qgmap_handle *h, int n, int its)
+// common prologue of a step: history capacity, options.its, iteration counter at the start
+int qgmap_prepare_step(qgmap_handle *h, int n, int its)
 {
     if (!h) return QGMAP_ERR_ARG;
     if (n < 0 || its < 1) QG_FAIL(h, QGMAP_ERR_ARG, "qgmap_step: n=%d its=%d", n, its);
@@ -412,16 +419,26 @@ extern "C" int qgmap_step_begin(qgmap_handle *h, int n, int its)
     int rc = ensure_hist(h, (int)std::min<long long>((long long)its, (long long)h->ctrl_host->it - 1 + n));
     if (rc) return rc;
     h->it0 = h->ctrl_host->it;
+    h->band_steps_enqueued = 0;
     if (h->ctrl_host->its != its) {
         h->ctrl_host->its = its;
         // the reference tests `it > its` after incrementing: a run resumed past its stops after one more iteration
         QG_CUDA(h, cudaMemcpyAsync(&h->ctrl->its, &h->ctrl_host->its, sizeof(int), cudaMemcpyHostToDevice, h->stream));
     }
+    return QGMAP_OK;
+}
+
+// enqueue up to n iterations on the handle's stream; returns without waiting
+extern "C" int qgmap_step_begin(qgmap_handle *h, int n, int its)
+{
+    if (h && h->in_group) QG_FAIL(h, QGMAP_ERR_STATE, "handle belongs to a qgmap_group: use qgmap_group_step");
+    int rc = qgmap_prepare_step(h, n, its);
+    if (rc) return rc;
     long long launches = 0;
     QG_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     int left = n;
     if (h->nranks > 1) {
-        for (; left > 0; --left) { if ((rc = qgmap_band_iteration(h, &launches)) != QGMAP_OK) return rc; }
+        for (; left > 0; --left) { if ((rc = qgmap_band_iteration(h, &launches)) != QGMAP_OK) return rc; ++launches; }
     } else {
         if (left >= kGraphLen && (rc = build_graph(h)) != QGMAP_OK) return rc;
         for (; left >= kGraphLen; left -= kGraphLen) { QG_CUDA(h, cudaGraphLaunch(h->graph, h->stream)); launches += kGraphLen; }
@@ -443,7 +460,8 @@ extern "C" int qgmap_step_end(qgmap_handle *h, double *energy, double *ptdmu, do
     QG_CUDA(h, cudaSetDevice(h->device));
     h->pending = false;
     QG_CUDA(h, cudaStreamSynchronize(h->stream));
-    QG_CUDA(h, cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+    cudaGetLastError();
     const int done = h->ctrl_host->it - h->it0;
     if (n_done) *n_done = done;
     if (stopped) *stopped = h->ctrl_host->stop;
@@ -456,6 +474,17 @@ extern "C" int qgmap_step_end(qgmap_handle *h, double *energy, double *ptdmu, do
         }
     if (any) QG_CUDA(h, cudaStreamSynchronize(h->stream));
     return QGMAP_OK;
+}
+
+// epilogue of a step whose iterations were enqueued by a group: fetch the control block, then as qgmap_step_end
+int qgmap_finish_step(qgmap_handle *h, double *energy, double *ptdmu, double *ptdsigma, int *n_done, int *stopped)
+{
+    QG_CUDA(h, cudaSetDevice(h->device));
+    QG_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    QG_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    QG_CUDA(h, cudaMemcpyAsync(h->ctrl_host, h->ctrl, sizeof(QgCtrl), cudaMemcpyDeviceToHost, h->stream));
+    h->pending = true;
+    return qgmap_step_end(h, energy, ptdmu, ptdsigma, n_done, stopped);
 }
 
 extern "C" int qgmap_step(qgmap_handle *h, int n, int its, double *energy, double *ptdmu, double *ptdsigma,

@@ -42,6 +42,8 @@ struct qgmap_handle {
     float last_ms = 0.f;
     long long last_launches = 0;
     int rank = 0, nranks = 1;
+    bool in_group = false;         // member of a single-process qgmap_group (stepped by the group only)
+    int band_steps_enqueued = 0;   // NCCL band mode: iterations enqueued since the last control-block read-back
     QgBand *band = nullptr;
     std::string err;
 };
@@ -67,6 +69,9 @@ int qgmap_band_refresh(qgmap_handle *h);                       // exchange halo 
 int qgmap_band_iteration(qgmap_handle *h, long long *launches); // one iteration incl. all-reduce + halo exchange
 void qgmap_launch_iteration(const qgmap_handle *h);             // plain iteration kernel launch on h->stream
 void qgmap_launch_advance(const qgmap_handle *h);
+int qgmap_prepare_step(qgmap_handle *h, int n, int its);
+int qgmap_finish_step(qgmap_handle *h, double *energy, double *ptdmu, double *ptdsigma, int *n_done, int *stopped);
+void qgmap_set_last_error(const char *msg);
 
 extern thread_local long long g_solve_launches;
 extern thread_local float g_solve_ms;

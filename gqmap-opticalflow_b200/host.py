@@ -280,3 +280,65 @@ def fp32_peak(device=-1):
     v = C.c_double(0)
     check(lib.qgmap_fp32_peak(int(device), C.byref(v)))
     return v.value
+
+
+class BandGroup:
+    """One frame pair split into row bands, all bands driven by this process: qgmap_group_* of the C ABI.
+    devices: list of CUDA ordinals, one per band (None: every band on the current device)."""
+
+    def __init__(self, options, I1, I2, nbands, devices=None, variant="full"):
+        self.variant = _lib.VARIANT_SUPER if variant in ("super", _lib.VARIANT_SUPER) else _lib.VARIANT_FULL
+        I1, I2 = _check_images(I1, I2, self.variant)
+        self.cfg = make_config(options, self.variant)
+        self._g = C.c_void_p(None)
+        dev = None
+        if devices is not None:
+            if len(devices) != nbands:
+                raise ValueError("devices must list one CUDA ordinal per band")
+            dev = (C.c_int * nbands)(*devices)
+        check(lib.qgmap_group_create(C.byref(self.cfg), dptr(I1), dptr(I2), I1.shape[0], I1.shape[1], int(nbands), dev, C.byref(self._g)))
+        M, N, L, nb = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        check(lib.qgmap_group_dims(self._g, C.byref(M), C.byref(N), C.byref(L), C.byref(nb)))
+        self.M, self.N, self.L, self.nbands = M.value, N.value, L.value, nb.value
+
+    def close(self):
+        if getattr(self, "_g", None) is not None and self._g.value:
+            lib.qgmap_group_destroy(self._g)
+            self._g = C.c_void_p(None)
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    _shape = Solver._shape
+
+    def set_state(self, state, T=None, it=1, alpha=None):
+        arrs = [f64(np.asarray(state[n], dtype=np.float64).reshape(self._shape(n), order="F")) for n in STATE_FIELDS]
+        al = None if alpha is None else np.ascontiguousarray(np.asarray(alpha, dtype=np.float64).ravel())
+        check(lib.qgmap_group_set_state(self._g, *(dptr(a) for a in arrs), dptr(al),
+                                        self.cfg.temperature if T is None else float(T), int(it)))
+
+    def init_state(self, seed=0):
+        check(lib.qgmap_group_init_state(self._g, C.c_uint64(int(seed))))
+
+    def get_state(self):
+        out = {n: np.zeros(self._shape(n), order="F") for n in STATE_FIELDS}
+        alpha = np.zeros(self.L)
+        T = C.c_double(0)
+        it = C.c_int(0)
+        check(lib.qgmap_group_get_state(self._g, *(dptr(out[n]) for n in STATE_FIELDS), dptr(alpha), C.byref(T), C.byref(it)))
+        out["alpha"], out["T"], out["it"] = alpha, T.value, it.value
+        return out
+
+    def step(self, n, its=2 ** 30):
+        E, dm, ds = np.zeros(max(n, 1)), np.zeros(max(n, 1)), np.zeros(max(n, 1))
+        done, stopped = C.c_int(0), C.c_int(0)
+        check(lib.qgmap_group_step(self._g, int(n), int(its), dptr(E), dptr(dm), dptr(ds), C.byref(done), C.byref(stopped)))
+        ms = C.c_float(0)
+        lib.qgmap_group_last_step_ms(self._g, C.byref(ms))
+        k = done.value
+        return dict(Energy=E[:k], ptdmu=dm[:k], ptdsigma=ds[:k], n_done=k, stopped=bool(stopped.value), ms=ms.value)

@@ -168,6 +168,23 @@ int qgmap_debug_gradients(qgmap_handle *h, double *G_muu, double *G_muv, double 
 int qgmap_band_unique_id(void *id128);
 int qgmap_band_connect(qgmap_handle *h, int rank, int nranks, const void *nccl_unique_id);
 
+/* The same decomposition driven by ONE process (the natural model for a MATLAB host; also how it is tested on one GPU):
+ * nbands handles, band b on devices[b] (NULL: all on the current device), halo rows copied peer-to-peer between the bands'
+ * state buffers, global sums combined in fixed band order.  State calls take / return the FULL-grid arrays of
+ * qgmap_set_state / qgmap_get_state; qgmap_group_step has the semantics of qgmap_step. */
+typedef struct qgmap_group qgmap_group;
+int qgmap_group_create(const qgmap_config *cfg, const double *I1, const double *I2, int Mo, int No, int nbands,
+                       const int *devices, qgmap_group **out);
+int qgmap_group_destroy(qgmap_group *g);
+int qgmap_group_dims(const qgmap_group *g, int *M, int *N, int *L, int *nbands);
+int qgmap_group_set_state(qgmap_group *g, const double *muu, const double *muv, const double *sigu, const double *sigv,
+                          const double *pn, const double *rou, const double *w, const double *alpha, double T, int it);
+int qgmap_group_init_state(qgmap_group *g, uint64_t seed);
+int qgmap_group_get_state(qgmap_group *g, double *muu, double *muv, double *sigu, double *sigv, double *pn, double *rou,
+                          double *w, double *alpha, double *T, int *it);
+int qgmap_group_step(qgmap_group *g, int n, int its, double *energy, double *ptdmu, double *ptdsigma, int *n_done, int *stopped);
+int qgmap_group_last_step_ms(const qgmap_group *g, float *ms);
+
 const char *qgmap_last_error(const qgmap_handle *h);   /* h may be NULL: last error of a handle-less call */
 const char *qgmap_status_string(int status);
 int qgmap_version(void);

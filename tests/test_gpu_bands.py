@@ -1,0 +1,46 @@
+"""Row-band decomposition on ONE GPU: nbands handles exchange halo rows and global sums through the same code
+path a multi-GPU single-process host uses (qgmap_group_*).  The N-band result must equal the 1-band result bit for bit in
+the beliefs (identical fp32 arithmetic per pixel) and to fp64 rounding in the reductions."""
+import numpy as np
+import pytest
+
+from conftest import make_problem, options_from_cfg, state_dict
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("variant,shape,L,K,T,nbands", [
+    ("full", (61, 70), 2, 3, 0.0, 2), ("full", (61, 70), 2, 3, 0.0, 3), ("full", (96, 45), 3, 5, 0.2, 4),
+    ("super", (96, 128), 2, 3, 0.2, 2), ("super", (128, 96), 3, 5, 0.2, 5),
+])
+def test_bands_match_single_domain(pkg, O, variant, shape, L, K, T, nbands):
+    sup = variant == "super"
+    Mo, No = shape
+    cfg, I1, I2, st = make_problem(O, Mo, No, L, K, super=sup, seed=5, T=T, small_sigma=True)
+    opts = options_from_cfg(cfg, T=T, alpha_scale=1e-5)
+    n = 14
+    with pkg.Solver(opts, I1, I2, variant=variant) as s:
+        s.set_state(state_dict(st), T=T, it=495)            # crosses it=500: alpha update and (super) anneal are exercised
+        r1 = s.step(n)
+        a = s.get_state()
+    with pkg.BandGroup(opts, I1, I2, nbands, variant=variant) as g:
+        assert g.nbands == nbands
+        g.set_state(state_dict(st), T=T, it=495)
+        rb = g.step(n)
+        b = g.get_state()
+    assert r1["n_done"] == rb["n_done"] == n
+    for f in ("muu", "muv", "sigmau", "sigmav", "pn", "rou"):
+        assert np.array_equal(a[f], b[f]), f                 # bit-identical beliefs, halo rows included
+    assert np.abs(rb["Energy"] / r1["Energy"] - 1).max() < 1e-12
+    assert np.abs(rb["ptdmu"] / r1["ptdmu"] - 1).max() < 1e-12
+    assert np.abs(a["alpha"] - b["alpha"]).max() < 1e-14 and a["it"] == b["it"] == 495 + n
+    assert a["T"] == b["T"]
+
+
+def test_band_group_stop_rule(pkg, O):
+    cfg, I1, I2, st = make_problem(O, 48, 40, 1, 3, seed=8)
+    with pkg.BandGroup(options_from_cfg(cfg), I1, I2, 3) as g:
+        g.set_state(state_dict(st))
+        r = g.step(10, its=6)
+        assert (r["n_done"], r["stopped"]) == (6, True)
+        assert g.step(3, its=6)["n_done"] == 0
