@@ -1,0 +1,60 @@
+"""Multi-process plumbing (one process per GPU, torch.distributed for the rendezvous): how the two natural splits of the
+path are laid over ranks.  torch.distributed is plumbing only: the data path of a row-band run is
+NCCL send/recv + all-reduce issued by libqgmap.so itself (qgmap_band_connect); independent frame pairs need no collective.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import check, lib
+
+
+def shard_pairs(n_pairs, rank, world):
+    """Indices of the frame pairs rank `rank` owns (contiguous blocks, sizes differ by at most one)."""
+    lo = n_pairs * rank // world
+    hi = n_pairs * (rank + 1) // world
+    return list(range(lo, hi))
+
+
+def band_rows(M, rank, world):
+    """Rows [row_begin,row_end) of an M-row belief grid owned by `rank` (same rule as qgmap_group_create)."""
+    if M // world < 2:
+        raise ValueError("%d bands over %d rows: need at least 2 rows per band" % (world, M))
+    return M * rank // world, M * (rank + 1) // world
+
+
+def new_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it; works without a GPU)."""
+    buf = C.create_string_buffer(128)
+    check(lib.qgmap_band_unique_id(buf))
+    return bytes(buf.raw)
+
+
+def broadcast_unique_id(dist, device=None):
+    """Rank 0 creates the NCCL id, every rank receives it through torch.distributed (gloo or nccl backend)."""
+    import torch
+    t = torch.zeros(128, dtype=torch.uint8, device=device if device is not None else "cpu")
+    if dist.get_rank() == 0:
+        t.copy_(torch.frombuffer(bytearray(new_unique_id()), dtype=torch.uint8))
+    dist.broadcast(t, src=0)
+    return bytes(t.cpu().numpy().tobytes())
+
+
+def connect_band(solver, dist, device=None):
+    """Attach a Solver created with options.row_begin/row_end = band_rows(M, rank, world) to its neighbours."""
+    uid = broadcast_unique_id(dist, device)
+    buf = C.create_string_buffer(uid, 128)
+    check(lib.qgmap_band_connect(solver._h, dist.get_rank(), dist.get_world_size(), buf), solver._h)
+
+
+def assemble_bands(dist, state, M):
+    """Every rank's get_state() fills only the rows it owns; gather the owned row blocks into full arrays on all ranks."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    rb, re = band_rows(M, rank, world)
+    mine = {k: np.ascontiguousarray(v[rb:re]) for k, v in state.items() if isinstance(v, np.ndarray) and v.ndim >= 3}
+    parts = [None] * world
+    dist.all_gather_object(parts, mine)
+    out = dict(state)
+    for k in mine:
+        out[k] = np.asfortranarray(np.concatenate([p[k] for p in parts], axis=0))
+    return out

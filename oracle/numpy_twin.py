@@ -102,7 +102,7 @@ def _spectral(tab, a, u1, u2, o1, o2, p, pot, T, kappa_sign, guard_a0):
     return da, du1, du2, do1, do2, dp, a * da
 
 
-def iteration_gradients(I1, VV, st, *, K, T, lambdad, lambdas, epsn, super_=False, guard_a0=True):
+def iteration_gradients(I1, VV, st, *, K, T, lambdad, lambdas, epsn, super_=False, guard_a0=True, row_off=0):
     """One gradient pass + assembly (G:29-40 / S:28-39).  `st` holds muu,muv,sigu,sigv,pn (M,N,L), rou (M,N,L,2,2),
     alpha (L,).  Returns dict of the 14 raw arrays, the assembled dmuu.. ('G_*'), dalpha, Energy, ptdmu, ptdsigma."""
     tab = tables(K)
@@ -110,7 +110,7 @@ def iteration_gradients(I1, VV, st, *, K, T, lambdad, lambdas, epsn, super_=Fals
     M, N, L = muu.shape
     alpha = np.asarray(st["alpha"]).reshape(1, 1, L)
     a3 = np.broadcast_to(alpha, (M, N, L))
-    ms = np.arange(1, M + 1).reshape(M, 1, 1)
+    ms = np.arange(1 + row_off, M + 1 + row_off).reshape(M, 1, 1)   # row_off: the arrays are rows [row_off, row_off+M) of a larger grid
     ns = np.arange(1, N + 1).reshape(1, N, 1)
 
     if super_:

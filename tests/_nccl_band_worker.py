@@ -1,0 +1,51 @@
+"""Worker for tests/test_gpu_multirank.py: one process per GPU, row bands of ONE frame pair over NCCL (qgmap_band_connect).
+Rank 0 also solves the undivided problem and checks the assembled band result is bit-identical."""
+import importlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("gloo")                       # rendezvous only; the data path is libqgmap's own NCCL communicator
+    rank, world = dist.get_rank(), dist.get_world_size()
+    pkg = importlib.import_module("gqmap-opticalflow_b200")
+    from oracle import oracle as O
+    from conftest import make_problem, options_from_cfg, state_dict
+    for variant, (Mo, No), L, K, T in (("full", (75, 90), 2, 5, 0.0), ("super", (128, 160), 3, 3, 0.2)):
+        sup = variant == "super"
+        cfg, I1, I2, st = make_problem(O, Mo, No, L, K, super=sup, seed=23, T=T, small_sigma=True)
+        rb, re = pkg.dist.band_rows(cfg.M, rank, world)
+        opts = options_from_cfg(cfg, T=T, alpha_scale=1e-5, device=local)
+        n = 12
+        with pkg.Solver(dict(opts, row_begin=rb, row_end=re), I1, I2, variant=variant) as s:
+            pkg.dist.connect_band(s, dist)
+            s.set_state(state_dict(st), T=T, it=495)
+            r = s.step(n)
+            full = pkg.dist.assemble_bands(dist, s.get_state(), cfg.M)
+        assert r["n_done"] == n, r
+        if rank == 0:
+            with pkg.Solver(opts, I1, I2, variant=variant) as s1:
+                s1.set_state(state_dict(st), T=T, it=495)
+                r1 = s1.step(n)
+                a = s1.get_state()
+            for f in ("muu", "muv", "sigmau", "sigmav", "pn", "rou"):
+                assert np.array_equal(a[f], full[f]), (variant, f, np.abs(a[f] - full[f]).max())
+            assert np.abs(r["Energy"] / r1["Energy"] - 1).max() < 1e-12
+            assert np.abs(full["alpha"] - a["alpha"]).max() < 1e-14
+            print("nccl bands %s world=%d: bit-identical to the single domain, %.3f ms/it" % (variant, world, r["ms"] / n), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
