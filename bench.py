@@ -252,6 +252,74 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_band4k(args):
+    """BASELINE configs[3]: ONE synthetic 3840x2160 frame pair, L=3, K=5, split into row bands over the ranks; per iteration
+    the boundary rows travel over NCCL/NVLink and 4L doubles are all-reduced (libqgmap's own communicator).  Strong scaling."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = importlib.import_module(PKG)
+    M, N, L, K = args.band_rows, args.band_cols, 3, 5
+    I1, I2, flow, (minu, maxu, minv, maxv) = pkg.synthetic_pair(M, N, seed=1234)
+    opts = dict(K=K, L=L, temperature=0.0, drate=0.5, epsn=1e-6, lambdad=1.0, lambdas=5.0, minu=minu, maxu=maxu, minv=minv,
+                maxv=maxv, device=local)
+    if world > 1:
+        rb, re = pkg.dist.band_rows(M, rank, world)
+        opts.update(row_begin=rb, row_end=re)
+    s = pkg.Solver(opts, I1, I2)
+    if world > 1:
+        pkg.dist.connect_band(s, dist, device=torch.device("cuda", local))
+    s.init_state(seed=4321)
+    iters = args.iters
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    if args.burnin > 0:
+        s.step(args.burnin)
+    for _ in range(args.warmup):
+        s.step(iters)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    ms, launches = 0.0, 0
+    for _ in range(args.steps):
+        r = s.step(iters)
+        ms += r["ms"]
+        launches += r["launches"]
+    barrier()
+    clocks = sampler.stop()
+    s.close()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    if rank == 0:
+        value = M * N * iters * args.steps / (ms_max * 1e-3)
+        F = flops_per_px_it(L, K)
+        fp32_meas = pkg.fp32_peak(local)
+        ach = value * F / 1e12 / world
+        print(json.dumps({
+            "metric": "QGMAP pixel-iterations/s", "value": value, "unit": "pixel-iter/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "one synthetic %dx%d frame pair, L=3, K=5, gqmap_gpu_mixture path, %d row band(s), 1-row halo exchange + "
+                                   "4L-double all-reduce per iteration over NCCL; %d iterations per step after %d burn-in" % (N, M, world, iters, args.burnin),
+                       "iters_per_step": iters, "parallelism": "row bands x%d" % world,
+                       "l2": "state 2 x %.0f MB + gather layout %.0f MB exceed the 126 MB L2" % (M * N * 9 * L * 4 / 1e6 / world, (M + 2) * N * 32 / 1e6)},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "roofline": {"bound": "fp32", "achieved": ach, "peak": fp32_meas, "unit": "TFLOP/s", "frac": ach / fp32_meas,
+                         "note": "per GPU; algorithmic %.0f flop per pixel-iteration" % F}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def cpu_baseline(pkg, items, budget_s=12.0, nthreads=0):
     """The oracle (kind 'port': fp64 C restatement of gqmap_gpu_mixture.m, OpenMP) timed on the host cores on a bounded
     sample: the RubberWhale-shaped pair of the same workload, as many whole iterations as fit the budget."""
@@ -333,15 +401,21 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--iters", type=int, default=200, help="ascent iterations per frame pair per step (device-resident leg)")
     ap.add_argument("--burnin", type=int, default=3000, help="untimed iterations per pair before the warm-up steps")
-    ap.add_argument("--e2e-its", type=int, default=2000, help="options.its of each end-to-end gqmap_gpu_mixture call")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-its", type=int, default=5000, help="options.its of each end-to-end gqmap_gpu_mixture call")
+    ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--ref-iters", type=int, default=1, help="reference arm: iterations per pair per step")
+    ap.add_argument("--workload", default="middlebury8", choices=["middlebury8", "band4k"],
+                    help="middlebury8 = BASELINE configs[1] (default, independent pairs sharded by rank); band4k = configs[3] (one 4K pair in row bands)")
+    ap.add_argument("--band-rows", type=int, default=2160)
+    ap.add_argument("--band-cols", type=int, default=3840)
     ap.add_argument("--ref-pairs", type=int, default=8, help="reference arm: how many of the 8 pairs form the bounded sample")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "band4k":
+        run_band4k(args)
     else:
         run_ours(args)
 
