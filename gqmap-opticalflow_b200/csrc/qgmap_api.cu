@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -68,7 +69,8 @@ extern "C" int qgmap_config_defaults(qgmap_config *c, int variant)
 // --------------------------------------------------------------------------------------------------------------------
 template <int KT, bool SUPER, bool DUMP>
 static void launch_inst(const qgmap_handle *h) {
-    qgmap_iter_kernel<KT, SUPER, DUMP><<<h->grid, dim3(QG_TW, QG_TH + 1), 0, h->stream>>>(h->params);
+    if (h->lanes_per_belief == 4) qgmap_iter_kernel_g4<KT, SUPER, DUMP><<<h->grid, dim3(QG_TW, QG_TH + 1), 0, h->stream>>>(h->params);
+    else qgmap_iter_kernel<KT, SUPER, DUMP><<<h->grid, dim3(QG_TW, QG_TH + 1), 0, h->stream>>>(h->params);
 }
 template <bool SUPER, bool DUMP>
 static void launch_k(const qgmap_handle *h) {
@@ -220,9 +222,19 @@ extern "C" int qgmap_create(const qgmap_config *cfg, const double *I1, const dou
         QG_CUDA_C(cudaGetLastError());
     }
 
-    // tiles
+    // tiles.  One thread per (belief pixel, component) when that fills the GPU; four lanes per belief (edge quadratures and
+    // node rows split over the lanes, combined by warp shuffles) when the belief grid is small.
     const int out_rows = std::max(h->out_r1 - h->out_r0, 0);
-    h->grid = dim3((N - 2 + QG_TW - 2) / (QG_TW - 1), std::max((out_rows + QG_TH - 1) / QG_TH, 1), h->L);
+    {
+        const char *env = getenv("QGMAP_LANES");
+        const long long beliefs = (long long)(N - 2) * std::max(out_rows, 1) * h->L;
+        // measured on B200 (profiles/): the 4-lane mapping only pays for the super-pixel variant on small grids (+3%); it costs
+        // ~40% at K=3 where the replicated per-lane prologue/epilogue outweighs the shorter sample loop
+        h->lanes_per_belief = env ? atoi(env) : ((sup && beliefs < 200000) ? 4 : 1);
+        if (h->lanes_per_belief != 4) h->lanes_per_belief = 1;
+    }
+    const int tw = h->lanes_per_belief == 4 ? QG_CW - 1 : QG_TW - 1;
+    h->grid = dim3((N - 2 + tw - 1) / tw, std::max((out_rows + QG_TH - 1) / QG_TH, 1), h->L);
     const size_t nblk = (size_t)h->grid.x * h->grid.y * h->grid.z;
     QG_CUDA_C(cudaMalloc(&h->partials, nblk * QG_NRED * sizeof(double)));
     QG_CUDA_C(cudaMemsetAsync(h->partials, 0, nblk * QG_NRED * sizeof(double), h->stream));

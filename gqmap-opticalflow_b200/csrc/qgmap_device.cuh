@@ -247,9 +247,10 @@ __device__ __forceinline__ float qg_super_sample(const QgTap8 *__restrict__ VV8,
 // ---- quadrature loops -------------------------------------------------------------------------------------------
 // Tensor-grid accumulation: the inner loop runs over XI = X(c) (k = r + K*c in the reference's column-major table,
 // :9), the outer over XJ = X(r).  F(x1,x2) returns the un-scaled potential magnitude; scale = -lambda.
+// r0/rstep: the XJ rows this lane evaluates (a group of lanes may share one belief, see qgmap_iter_kernel_g4).
 template <int KT, class F>
 __device__ __forceinline__ QgMoments qg_quadrature(const QgTables &tab, int Krt, float u1, float u2, float o1, float o2,
-                                                   const QgSpectral &sp, float scale, F pot)
+                                                   const QgSpectral &sp, float scale, F pot, int r0 = 0, int rstep = 1)
 {
     const float sqrt2 = 1.4142135623730951f;
     const int K = KT > 0 ? KT : Krt;
@@ -257,7 +258,7 @@ __device__ __forceinline__ QgMoments qg_quadrature(const QgTables &tab, int Krt,
     const float a2s = sqrt2 * o2 * sp.s, a2t = sqrt2 * o2 * sp.t;     // x2 = u2 + a2t*XI + a2s*XJ
     QgMoments m = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-    for (int r = 0; r < K; ++r) {
+    for (int r = r0; r < K; r += rstep) {
         const float xj = tab.X[r];
         const float b1 = fmaf(a1t, xj, u1), b2 = fmaf(a2s, xj, u2);
         float S0 = 0.f, S1 = 0.f, S2 = 0.f;

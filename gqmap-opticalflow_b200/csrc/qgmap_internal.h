@@ -38,6 +38,7 @@ struct qgmap_handle {
     bool has_unknown = false, has_state = false;
     QgIterParams params{};
     dim3 grid{};
+    int lanes_per_belief = 1;     // 1: qgmap_iter_kernel, 4: qgmap_iter_kernel_g4
     cudaGraphExec_t graph = nullptr;
     float last_ms = 0.f;
     long long last_launches = 0;

@@ -22,6 +22,73 @@ __device__ __forceinline__ float qg_warp_sum(float v) {
     return v;
 }
 
+// Block partial sums (fp32 within a warp, fp64 across warps and blocks) of red[] = {energy, dalpha, |G_muu|, |G_sigu|}; the
+// last block to finish reduces all partials in a fixed order and advances the control block (:36,:48,:50,:69-75).
+template <bool DUMP>
+__device__ __forceinline__ void qg_block_finish(const QgIterParams &p, QgCtrl *ctrl, const float (&red)[QG_NRED], int r, int j)
+{
+    __shared__ double sh_red[QG_TH + 1][QG_NRED];
+    __shared__ int sh_last;
+#pragma unroll
+    for (int k = 0; k < QG_NRED; ++k) {
+        float v = qg_warp_sum(red[k]);
+        if (j == 0) sh_red[r][k] = (double)v;
+    }
+    __syncthreads();
+    const int tid = r * QG_TW + j;
+    const unsigned int nblk_l = gridDim.x * gridDim.y;
+    const unsigned int blk = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (tid < QG_NRED) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 1; w <= QG_TH; ++w) s += sh_red[w][tid];
+        p.partials[(size_t)blk * QG_NRED + tid] = s;
+    }
+    if (DUMP) return;
+
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int t = atomicAdd(&ctrl->ticket, 1u);
+        sh_last = (t == nblk_l * gridDim.z - 1);
+    }
+    __syncthreads();
+    if (!sh_last) return;
+    __threadfence();
+    __shared__ double sh_sum[QG_LMAX * QG_NRED];
+    const int nthr = QG_TW * (QG_TH + 1), warp = tid >> 5, lane = tid & 31, nwarp = nthr / 32;
+    for (int ll = 0; ll < p.L; ++ll) {
+        double acc[QG_NRED] = {0.0, 0.0, 0.0, 0.0};
+        const double *pp = p.partials + (size_t)ll * nblk_l * QG_NRED;
+        for (unsigned int b = tid; b < nblk_l; b += nthr) {
+#pragma unroll
+            for (int k = 0; k < QG_NRED; ++k) acc[k] += __ldcg(pp + (size_t)b * QG_NRED + k);
+        }
+#pragma unroll
+        for (int k = 0; k < QG_NRED; ++k) {
+            double v = acc[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) sh_red[warp][k] = v;
+        }
+        __syncthreads();
+        if (tid < QG_NRED) {
+            double s = 0.0;
+            for (int w = 0; w < nwarp; ++w) s += sh_red[w][tid];
+            sh_sum[ll * QG_NRED + tid] = s;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        ctrl->ticket = 0;
+        if (p.band) {
+            for (int k = 0; k < p.L * QG_NRED; ++k) ctrl->sums[k] = sh_sum[k];   // summed across bands / ranks, then
+        } else {                                                               // the advance kernel runs qg_advance
+            qg_advance(p, ctrl, sh_sum);
+        }
+    }
+}
+
 template <int KT, bool SUPER, bool DUMP>
 __global__ void __launch_bounds__(QG_TW *(QG_TH + 1), SUPER ? 2 : 3)
 qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
@@ -85,8 +152,6 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
     // ---- endpoint-2 exchange (before the node term: the warps of a CTA then never wait for each other again until the
     //      final block reduction, and the cheap halo warp does not stall the barrier) ---------------------------------
     __shared__ float4 sh_dn[QG_TH + 1][QG_TW];
-    __shared__ double sh_red[QG_TH + 1][QG_NRED];
-    __shared__ int sh_last;
     sh_dn[r][j] = make_float4(gdu.du2, gdu.do2, gdv.du2, gdv.do2);          // to pixel (m+1,n)
     const float lf_du_u = __shfl_up_sync(0xffffffffu, gru.du2, 1);             // from pixel (m,n-1)
     const float lf_do_u = __shfl_up_sync(0xffffffffu, gru.do2, 1);
@@ -159,65 +224,143 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
         }
     }
 
-    // ---- block partial sums (fp32 within a warp, fp64 across warps and blocks) ------------------------------------
-#pragma unroll
-    for (int k = 0; k < QG_NRED; ++k) {
-        float v = qg_warp_sum(red[k]);
-        if (j == 0) sh_red[r][k] = (double)v;
-    }
-    __syncthreads();
-    const int tid = r * QG_TW + j;
-    const unsigned int nblk_l = gridDim.x * gridDim.y;
-    const unsigned int blk = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-    if (tid < QG_NRED) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 1; w <= QG_TH; ++w) s += sh_red[w][tid];
-        p.partials[(size_t)blk * QG_NRED + tid] = s;
-    }
-    if (DUMP) return;
-
-    // ---- last block: deterministic global reduction + control advance --------------------------------------------
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        unsigned int t = atomicAdd(&ctrl->ticket, 1u);
-        sh_last = (t == nblk_l * gridDim.z - 1);
-    }
-    __syncthreads();
-    if (!sh_last) return;
-    __threadfence();
-    __shared__ double sh_sum[QG_LMAX * QG_NRED];
-    const int nthr = QG_TW * (QG_TH + 1), warp = tid >> 5, lane = tid & 31, nwarp = nthr / 32;
-    for (int ll = 0; ll < p.L; ++ll) {
-        double acc[QG_NRED] = {0.0, 0.0, 0.0, 0.0};
-        const double *pp = p.partials + (size_t)ll * nblk_l * QG_NRED;
-        for (unsigned int b = tid; b < nblk_l; b += nthr) {
-#pragma unroll
-            for (int k = 0; k < QG_NRED; ++k) acc[k] += __ldcg(pp + (size_t)b * QG_NRED + k);
-        }
-#pragma unroll
-        for (int k = 0; k < QG_NRED; ++k) {
-            double v = acc[k];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) sh_red[warp][k] = v;
-        }
-        __syncthreads();
-        if (tid < QG_NRED) {
-            double s = 0.0;
-            for (int w = 0; w < nwarp; ++w) s += sh_red[w][tid];
-            sh_sum[ll * QG_NRED + tid] = s;
-        }
-        __syncthreads();
-    }
-    if (tid == 0) {
-        ctrl->ticket = 0;
-        if (p.band) {
-            for (int k = 0; k < p.L * QG_NRED; ++k) ctrl->sums[k] = sh_sum[k];   // all-reduced across ranks, then
-        } else {                                                               // qgmap_advance_kernel runs qg_advance
-            qg_advance(p, ctrl, sh_sum);
-        }
-    }
+    qg_block_finish<DUMP>(p, ctrl, red, r, j);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Four lanes per (belief pixel, component).  Used when the belief grid is too small to fill 148 SMs with one thread per
+// belief (the super-pixel variant has 1/16 of the beliefs but 16x the work per node sample; small frames with few
+// components): lane g of a group evaluates edge quadrature q = g (q = e + 2c: down-u, right-u, down-v, right-v -- the four
+// are perfectly balanced) and the XJ rows r = g, g+4, ... of the node quadrature; the six node moments are combined with
+// two xor-shuffles, the edge gradients with one or two (north_star: "warp-shuffle reductions of the gradients").
+// A warp covers 8 columns (column group 0 = halo column); tile = 7 x QG_TH outputs.
+#define QG_G 4
+#define QG_CW (QG_TW / QG_G)
+
+template <int KT, bool SUPER, bool DUMP>
+__global__ void __launch_bounds__(QG_TW *(QG_TH + 1), SUPER ? 2 : 3)
+qgmap_iter_kernel_g4(const __grid_constant__ QgIterParams p)
+{
+    QgCtrl *ctrl = p.ctrl;
+    if (!DUMP && ctrl->stop) return;
+    const int it = ctrl->it;
+    const float *__restrict__ in = p.buf[(it - 1) & 1];
+    float *__restrict__ out = p.buf[it & 1];
+
+    const int j = threadIdx.x, r = threadIdx.y;
+    const int jc = j / QG_G, g = j % QG_G;                         // column group within the warp, lane within the group
+    const int e = g & 1, c = g >> 1;                               // this lane's edge: e 0=down 1=right, layer c 0=u 1=v
+    const int l = blockIdx.z;
+    const int n = (int)blockIdx.x * (QG_CW - 1) + jc;              // global column (group 0 = halo column n0-1)
+    const int m = p.out_r0 + (int)blockIdx.y * QG_TH + r - 1;      // global row    (warp 0 = halo row m0-1)
+    const bool incol = (n >= 1) && (n <= p.N - 2);
+    const bool inrow = (m >= p.out_r0) && (m < p.out_r1);
+    const bool is_out = (r >= 1) && (jc >= 1) && inrow && incol;
+    const bool need_down = is_out || ((r == 0) && (jc >= 1) && incol && (m + 1 < p.out_r1));
+    const bool need_right = is_out || ((jc == 0) && (r >= 1) && inrow && (n + 1 <= p.N - 2));
+    const bool my_edge = e ? need_right : need_down;
+
+    const float a = (float)ctrl->alpha[l];
+    const float T = (float)ctrl->T;
+    const float step = (float)(p.step0 / (1.0 + (double)it / p.step_tau));      // :27
+    const long long pl = p.plane;
+    const float *base = in + (long long)l * pl;
+    const long long idx = (long long)(m - p.g0) * p.P + n;
+    const long long fstr = (long long)p.L * pl;
+
+    // ---- this lane's edge quadrature (:31-34) ----------------------------------------------------------------------
+    QgGrad ge = {};
+    float rouq = 0.f;
+    if (my_edge) {
+        const long long inb = idx + (e ? 1 : p.P);
+        const float *mu = base + (c ? F_MUV : F_MUU) * fstr, *sg = base + (c ? F_SIGV : F_SIGU) * fstr;
+        rouq = __ldg(base + (F_ROU0 + g) * fstr + idx);
+        ge = qg_edge<KT>(p.tab, p.K, a, __ldg(mu + idx), __ldg(mu + inb), __ldg(sg + idx), __ldg(sg + inb), rouq, p.lambdas, p.epsn, T);
+    }
+    // ---- endpoint-2 exchange: down edges through shared memory to the row below, right edges by shuffle to the next group
+    __shared__ float sh_dn[QG_TH + 1][QG_CW][4];
+    if (e == 0) { sh_dn[r][jc][2 * c] = ge.du2; sh_dn[r][jc][2 * c + 1] = ge.do2; }
+    const float lf_du = __shfl_up_sync(0xffffffffu, ge.du2, QG_G);            // lanes e==1: right edge of pixel (m,n-1), same layer
+    const float lf_do = __shfl_up_sync(0xffffffffu, ge.do2, QG_G);
+    __syncthreads();
+
+    // per-lane share of the folded edge gradients (:37-40): layer c of this lane
+    float pm = ge.du1, ps = ge.do1;
+    if (is_out) {
+        if (e == 0) { pm += sh_dn[r - 1][jc][2 * c]; ps += sh_dn[r - 1][jc][2 * c + 1]; }
+        else        { pm += lf_du; ps += lf_do; }
+    }
+    const float E_mu = pm + __shfl_xor_sync(0xffffffffu, pm, 1);             // lanes (g, g^1) share the layer
+    const float E_sig = ps + __shfl_xor_sync(0xffffffffu, ps, 1);
+    float E_e = ge.Ei + __shfl_xor_sync(0xffffffffu, ge.Ei, 1);
+    E_e += __shfl_xor_sync(0xffffffffu, E_e, 2);                              // :48 edge part, all four edges
+    float E_a = ge.da + __shfl_xor_sync(0xffffffffu, ge.da, 1);
+    E_a += __shfl_xor_sync(0xffffffffu, E_a, 2);                              // :36 edge part
+
+    float red[QG_NRED] = {0.f, 0.f, 0.f, 0.f};
+    float *o = out + (long long)l * pl + idx;
+    float *d = DUMP ? p.dbg + (long long)l * pl + idx : nullptr;
+    if (is_out) {
+        if (DUMP) d[(5 + g) * fstr] = ge.dp;
+        else o[(F_ROU0 + g) * fstr] = qg_clamp(fmaf(ge.dp, step, rouq), -p.corr_tor, p.corr_tor);     // :45
+    }
+    // ---- node term (:29, :87-116): XJ rows g, g+4, ... on this lane; all 32 lanes take part in the shuffles ---------
+    float muu = 0.f, muv = 0.f, sigu = 1.f, sigv = 1.f, pn = 0.f;
+    QgMoments mo = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    QgSpectral sp;
+    if (is_out) {
+        muu = __ldg(base + F_MUU * fstr + idx);  muv = __ldg(base + F_MUV * fstr + idx);
+        sigu = __ldg(base + F_SIGU * fstr + idx); sigv = __ldg(base + F_SIGV * fstr + idx);
+        pn = __ldg(base + F_PN * fstr + idx);
+    }
+    sp.set(pn);
+    if (is_out) {
+        if (SUPER) {
+            float I1b[16];
+            const float *ip = p.I1 + (long long)(4 * m) * p.pitchI + 4 * n;
+#pragma unroll
+            for (int di = 0; di < 4; ++di) {
+                float4 v = __ldg(reinterpret_cast<const float4 *>(ip + (long long)di * p.pitchI));
+                I1b[di * 4 + 0] = v.x; I1b[di * 4 + 1] = v.y; I1b[di * 4 + 2] = v.z; I1b[di * 4 + 3] = v.w;
+            }
+            const int lastx = p.No - 2, lasty = p.Mo - 2, m4 = 4 * m, n4 = 4 * n;
+            mo = qg_quadrature<KT>(p.tab, p.K, muu, muv, sigu, sigv, sp, -p.lambdad, [&](float x1, float x2) {
+                return qg_super_sample(p.VV8, p.pitchV, m4, n4, lastx, lasty, x1, x2, I1b, p.epsn);
+            }, g, QG_G);
+        } else {
+            const float I1v = __ldg(p.I1 + (long long)m * p.pitchI + n);
+            const int lastx = p.No - 2, lasty = p.Mo - 2;
+            mo = qg_quadrature<KT>(p.tab, p.K, muu, muv, sigu, sigv, sp, -p.lambdad, [&](float x1, float x2) {
+                return qg_node_sample(p.VV8, p.pitchV, m, n, lastx, lasty, x1, x2, I1v, p.epsn);
+            }, g, QG_G);
+        }
+    }
+#pragma unroll
+    for (int sft = 1; sft < QG_G; sft <<= 1) {                                 // combine the four lanes' partial moments
+        mo.E += __shfl_xor_sync(0xffffffffu, mo.E, sft);   mo.MI += __shfl_xor_sync(0xffffffffu, mo.MI, sft);
+        mo.MJ += __shfl_xor_sync(0xffffffffu, mo.MJ, sft); mo.MII += __shfl_xor_sync(0xffffffffu, mo.MII, sft);
+        mo.MJJ += __shfl_xor_sync(0xffffffffu, mo.MJJ, sft); mo.MB += __shfl_xor_sync(0xffffffffu, mo.MB, sft);
+    }
+    if (is_out) {
+        const QgGrad gn = qg_epilogue(mo, sp, a, sigu, sigv, pn, -3.0f * T);
+        // lanes of layer c hold E_mu / E_sig of that layer: g=0 finishes (mu_u, sig_u, pn, sums), g=2 finishes (mu_v, sig_v)
+        const float G_mu = (c ? gn.du2 : gn.du1) + E_mu, G_sig = (c ? gn.do2 : gn.do1) + E_sig;
+        if (g == 0) {
+            const float e_px = gn.Ei + E_e, da_px = gn.da + E_a;
+            red[0] = e_px; red[1] = da_px; red[2] = fabsf(G_mu); red[3] = fabsf(G_sig);
+            if (DUMP) { d[0 * fstr] = G_mu; d[2 * fstr] = G_sig; d[4 * fstr] = gn.dp; d[9 * fstr] = e_px; d[10 * fstr] = da_px; }
+            else {
+                o[F_MUU * fstr] = qg_clamp(fmaf(G_mu, step, muu), p.minu, p.maxu);
+                o[F_SIGU * fstr] = qg_clamp(fmaf(G_sig, step, sigu), p.sig_min, p.sig_max);
+                o[F_PN * fstr] = qg_clamp(fmaf(gn.dp, step, pn), -p.corr_tor, p.corr_tor);
+            }
+        } else if (g == 2) {
+            if (DUMP) { d[1 * fstr] = G_mu; d[3 * fstr] = G_sig; }
+            else {
+                o[F_MUV * fstr] = qg_clamp(fmaf(G_mu, step, muv), p.minv, p.maxv);
+                o[F_SIGV * fstr] = qg_clamp(fmaf(G_sig, step, sigv), p.sig_min, p.sig_max);
+            }
+        }
+    }
+    qg_block_finish<DUMP>(p, ctrl, red, r, j);
+}

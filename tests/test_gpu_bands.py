@@ -9,6 +9,14 @@ from conftest import make_problem, options_from_cfg, state_dict
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["1", "4"], ids=["lanes1", "lanes4"])
+def lanes_per_belief(request, monkeypatch):
+    """Run every test with both thread mappings of the iteration kernel (one thread / four lanes per belief); without the
+    override the library picks by problem size and small test problems would only ever exercise the 4-lane kernel."""
+    monkeypatch.setenv("QGMAP_LANES", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("variant,shape,L,K,T,nbands", [
     ("full", (61, 70), 2, 3, 0.0, 2), ("full", (61, 70), 2, 3, 0.0, 3), ("full", (96, 45), 3, 5, 0.2, 4),
     ("super", (96, 128), 2, 3, 0.2, 2), ("super", (128, 96), 3, 5, 0.2, 5),

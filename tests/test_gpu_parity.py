@@ -10,6 +10,14 @@ from conftest import make_problem, options_from_cfg, state_dict
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=["1", "4"], ids=["lanes1", "lanes4"])
+def lanes_per_belief(request, monkeypatch):
+    """Run every test with both thread mappings of the iteration kernel (one thread / four lanes per belief); without the
+    override the library picks by problem size and small test problems would only ever exercise the 4-lane kernel."""
+    monkeypatch.setenv("QGMAP_LANES", request.param)
+    return request.param
+
 GRAD_RTOL = 3e-4        # of max|array| (fp32 vs fp64, cancellation in the score-function sums)
 
 
