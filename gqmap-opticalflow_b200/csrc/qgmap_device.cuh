@@ -172,19 +172,32 @@ __device__ __forceinline__ float qg_dot4(const float4 v, float a0, float a1, flo
 
 // sqrt(eps + (I1 - bicubic(VV))^2) at displacement (x1 horizontal, x2 vertical) from pixel (m,n) (0-based).
 // node_pot = -lambdad * this  (gqmap_gpu_mixture.m:156-179).
+// The 4x4 tap block of the cell a thread sampled last.  Once the beliefs have converged (sigma << 1 px) all K*K quadrature
+// points of a component fall into one or two cells, so the 16 taps are re-used from registers and the two 256-bit loads are
+// predicated off: the L1 gather -- the kernel's co-bottleneck while the beliefs are still scattered -- disappears.
+struct QgTapCache {
+    int ix, iy;
+    QgTap8 v01, v23;
+    __device__ __forceinline__ QgTapCache() : ix(-0x40000000), iy(-0x40000000) {}
+};
+
 __device__ __forceinline__ float qg_node_sample(const QgTap8 *__restrict__ VV8, int pitchV, int m, int n, int lastx,
-                                                int lasty, float x1, float x2, float I1v, float epsn)
+                                                int lasty, float x1, float x2, float I1v, float epsn, QgTapCache &tc)
 {
     float so, to;
     const int ix = qg_cell(n, x1, lastx, so);
     const int iy = qg_cell(m, x2, lasty, to);
-    const QgTap8 *r0 = VV8 + (long long)iy * pitchV + ix;    // padded coords: taps rows iy..iy+3, cols ix..ix+3
-    const QgTap8 v01 = qg_ld256(r0), v23 = qg_ld256(r0 + 2 * pitchV);
+    if (ix != tc.ix || iy != tc.iy) {
+        const QgTap8 *r0 = VV8 + (long long)iy * pitchV + ix;    // padded coords: taps rows iy..iy+3, cols ix..ix+3
+        tc.v01 = qg_ld256(r0);
+        tc.v23 = qg_ld256(r0 + 2 * pitchV);
+        tc.ix = ix; tc.iy = iy;
+    }
     float a0, a1, a2, a3, b0, b1, b2, b3;
     qg_cubic_w(so, a0, a1, a2, a3);
     qg_cubic_w(to, b0, b1, b2, b3);
-    const float h0 = qg_dot4(v01.r0, a0, a1, a2, a3), h1 = qg_dot4(v01.r1, a0, a1, a2, a3);
-    const float h2 = qg_dot4(v23.r0, a0, a1, a2, a3), h3 = qg_dot4(v23.r1, a0, a1, a2, a3);
+    const float h0 = qg_dot4(tc.v01.r0, a0, a1, a2, a3), h1 = qg_dot4(tc.v01.r1, a0, a1, a2, a3);
+    const float h2 = qg_dot4(tc.v23.r0, a0, a1, a2, a3), h3 = qg_dot4(tc.v23.r1, a0, a1, a2, a3);
     const float v = fmaf(h3, b3, fmaf(h2, b2, fmaf(h1, b1, h0 * b0)));
     const float d = fmaf(-0.25f, v, I1v);
     return qg_sqrt(fmaf(d, d, epsn));
@@ -239,7 +252,7 @@ __device__ __forceinline__ float qg_super_sample(const QgTap8 *__restrict__ VV8,
         for (int di = 0; di < 4; ++di)
 #pragma unroll 1
             for (int dj = 0; dj < 4; ++dj)
-                acc += qg_node_sample(VV8, pitchV, m4 + di, n4 + dj, lastx, lasty, x1, x2, I1b[di * 4 + dj], epsn);
+                { QgTapCache tc; acc += qg_node_sample(VV8, pitchV, m4 + di, n4 + dj, lastx, lasty, x1, x2, I1b[di * 4 + dj], epsn, tc); }
     }
     return acc;
 }

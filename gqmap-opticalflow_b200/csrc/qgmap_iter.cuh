@@ -201,8 +201,9 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
         } else {
             const float I1v = __ldg(p.I1 + (long long)m * p.pitchI + n);
             const int lastx = p.No - 2, lasty = p.Mo - 2;
+            QgTapCache tc;
             mo = qg_quadrature<KT>(p.tab, p.K, muu, muv, sigu, sigv, sp, -p.lambdad, [&](float x1, float x2) {
-                return qg_node_sample(p.VV8, p.pitchV, m, n, lastx, lasty, x1, x2, I1v, p.epsn);
+                return qg_node_sample(p.VV8, p.pitchV, m, n, lastx, lasty, x1, x2, I1v, p.epsn, tc);
             });
         }
         const QgGrad gn = qg_epilogue(mo, sp, a, sigu, sigv, pn, -3.0f * T);
@@ -330,8 +331,9 @@ qgmap_iter_kernel_g4(const __grid_constant__ QgIterParams p)
         } else {
             const float I1v = __ldg(p.I1 + (long long)m * p.pitchI + n);
             const int lastx = p.No - 2, lasty = p.Mo - 2;
+            QgTapCache tc;
             mo = qg_quadrature<KT>(p.tab, p.K, muu, muv, sigu, sigv, sp, -p.lambdad, [&](float x1, float x2) {
-                return qg_node_sample(p.VV8, p.pitchV, m, n, lastx, lasty, x1, x2, I1v, p.epsn);
+                return qg_node_sample(p.VV8, p.pitchV, m, n, lastx, lasty, x1, x2, I1v, p.epsn, tc);
             }, g, QG_G);
         }
     }
