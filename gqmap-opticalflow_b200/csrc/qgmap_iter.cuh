@@ -129,25 +129,25 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
     QgGrad gdu = {}, gdv = {}, gru = {}, grv = {};
     float rou0 = 0.f, rou1 = 0.f, rou2 = 0.f, rou3 = 0.f;
 
-    // ---- down edge (m,n)->(m+1,n), layers u and v  (:31-34, e=1) ------------------------------------------------
+    // ---- down edge (m,n)->(m+1,n), layers u and v as one fp32x2 stream  (:31-34, e=1) ----------------------------------
     if (need_down) {
         const long long idn = idx + p.P;
         rou0 = __ldg(base + F_ROU0 * fstr + idx);
         rou2 = __ldg(base + F_ROU2 * fstr + idx);
-        gdu = qg_edge<KT>(p.tab, p.K, a, muu, __ldg(base + F_MUU * fstr + idn), sigu, __ldg(base + F_SIGU * fstr + idn),
-                          rou0, p.lambdas, p.epsn, T);
-        gdv = qg_edge<KT>(p.tab, p.K, a, muv, __ldg(base + F_MUV * fstr + idn), sigv, __ldg(base + F_SIGV * fstr + idn),
-                          rou2, p.lambdas, p.epsn, T);
+        qg_edge2<KT>(p.tab, p.K, a, make_float2(muu, muv),
+                     make_float2(__ldg(base + F_MUU * fstr + idn), __ldg(base + F_MUV * fstr + idn)), make_float2(sigu, sigv),
+                     make_float2(__ldg(base + F_SIGU * fstr + idn), __ldg(base + F_SIGV * fstr + idn)), make_float2(rou0, rou2),
+                     p.lambdas, p.epsn, T, gdu, gdv);
     }
     // ---- right edge (m,n)->(m,n+1)  (e=2) -----------------------------------------------------------------------
     if (need_right) {
         const long long irt = idx + 1;
         rou1 = __ldg(base + F_ROU1 * fstr + idx);
         rou3 = __ldg(base + F_ROU3 * fstr + idx);
-        gru = qg_edge<KT>(p.tab, p.K, a, muu, __ldg(base + F_MUU * fstr + irt), sigu, __ldg(base + F_SIGU * fstr + irt),
-                          rou1, p.lambdas, p.epsn, T);
-        grv = qg_edge<KT>(p.tab, p.K, a, muv, __ldg(base + F_MUV * fstr + irt), sigv, __ldg(base + F_SIGV * fstr + irt),
-                          rou3, p.lambdas, p.epsn, T);
+        qg_edge2<KT>(p.tab, p.K, a, make_float2(muu, muv),
+                     make_float2(__ldg(base + F_MUU * fstr + irt), __ldg(base + F_MUV * fstr + irt)), make_float2(sigu, sigv),
+                     make_float2(__ldg(base + F_SIGU * fstr + irt), __ldg(base + F_SIGV * fstr + irt)), make_float2(rou1, rou3),
+                     p.lambdas, p.epsn, T, gru, grv);
     }
     // ---- endpoint-2 exchange (before the node term: the warps of a CTA then never wait for each other again until the
     //      final block reduction, and the cheap halo warp does not stall the barrier) ---------------------------------
@@ -195,15 +195,15 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
                 I1b[di * 4 + 0] = v.x; I1b[di * 4 + 1] = v.y; I1b[di * 4 + 2] = v.z; I1b[di * 4 + 3] = v.w;
             }
             const int lastx = p.No - 2, lasty = p.Mo - 2, m4 = 4 * m, n4 = 4 * n;
-            mo = qg_quadrature<KT>(p.tab, p.K, muu, muv, sigu, sigv, sp, -p.lambdad, [&](float x1, float x2) {
-                return qg_super_sample(p.VV8, p.pitchV, m4, n4, lastx, lasty, x1, x2, I1b, p.epsn);
+            mo = qg_quadrature<KT>(p.tab, p.K, muu, muv, sigu, sigv, sp, -p.lambdad, [&](float2 x) {
+                return qg_super_sample(p.VV8, p.pitchV, m4, n4, lastx, lasty, x, I1b, p.epsn);
             });
         } else {
             const float I1v = __ldg(p.I1 + (long long)m * p.pitchI + n);
             const int lastx = p.No - 2, lasty = p.Mo - 2;
             QgTapCache tc;
-            mo = qg_quadrature<KT>(p.tab, p.K, muu, muv, sigu, sigv, sp, -p.lambdad, [&](float x1, float x2) {
-                return qg_node_sample(p.VV8, p.pitchV, m, n, lastx, lasty, x1, x2, I1v, p.epsn, tc);
+            mo = qg_quadrature<KT>(p.tab, p.K, muu, muv, sigu, sigv, sp, -p.lambdad, [&](float2 x) {
+                return qg_node_sample(p.VV8, p.pitchV, m, n, lastx, lasty, x, I1v, p.epsn, tc);
             });
         }
         const QgGrad gn = qg_epilogue(mo, sp, a, sigu, sigv, pn, -3.0f * T);
@@ -325,15 +325,15 @@ qgmap_iter_kernel_g4(const __grid_constant__ QgIterParams p)
                 I1b[di * 4 + 0] = v.x; I1b[di * 4 + 1] = v.y; I1b[di * 4 + 2] = v.z; I1b[di * 4 + 3] = v.w;
             }
             const int lastx = p.No - 2, lasty = p.Mo - 2, m4 = 4 * m, n4 = 4 * n;
-            mo = qg_quadrature<KT>(p.tab, p.K, muu, muv, sigu, sigv, sp, -p.lambdad, [&](float x1, float x2) {
-                return qg_super_sample(p.VV8, p.pitchV, m4, n4, lastx, lasty, x1, x2, I1b, p.epsn);
+            mo = qg_quadrature<KT>(p.tab, p.K, muu, muv, sigu, sigv, sp, -p.lambdad, [&](float2 x) {
+                return qg_super_sample(p.VV8, p.pitchV, m4, n4, lastx, lasty, x, I1b, p.epsn);
             }, g, QG_G);
         } else {
             const float I1v = __ldg(p.I1 + (long long)m * p.pitchI + n);
             const int lastx = p.No - 2, lasty = p.Mo - 2;
             QgTapCache tc;
-            mo = qg_quadrature<KT>(p.tab, p.K, muu, muv, sigu, sigv, sp, -p.lambdad, [&](float x1, float x2) {
-                return qg_node_sample(p.VV8, p.pitchV, m, n, lastx, lasty, x1, x2, I1v, p.epsn, tc);
+            mo = qg_quadrature<KT>(p.tab, p.K, muu, muv, sigu, sigv, sp, -p.lambdad, [&](float2 x) {
+                return qg_node_sample(p.VV8, p.pitchV, m, n, lastx, lasty, x, I1v, p.epsn, tc);
             }, g, QG_G);
         }
     }

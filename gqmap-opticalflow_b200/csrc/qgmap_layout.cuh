@@ -70,8 +70,8 @@ __global__ void qgmap_cast_kernel(const double *__restrict__ src, T *__restrict_
         dst[t] = (T)src[t];
 }
 
-// Packed second frame for the iteration kernel: out[y*pitch8 + x] = { VV(y, x..x+3), VV(y+1, x..x+3) } (zero beyond the
-// padded image), y = 0..rows-1 entries.
+// Packed second frame for the iteration kernel (QgTap8): entry (y,x) = rows y, y+1 x columns x..x+3, interleaved by row inside
+// each column: out[8*(y*pitch8+x) + 2c + {0,1}] = VV(y + {0,1}, x + c)  (zero beyond the padded image), y = 0..rows_out-1.
 static __global__ void qgmap_pack8_kernel(const double *__restrict__ VV, int pitchV, int rows_src, int width, float4 *__restrict__ out,
                                           int pitch8, int rows_out)
 {
@@ -79,6 +79,6 @@ static __global__ void qgmap_pack8_kernel(const double *__restrict__ VV, int pit
     if (x >= pitch8 || y >= rows_out) return;
     auto g = [&](int r, int c) -> float { return (r < rows_src && c < width) ? (float)VV[(long long)r * pitchV + c] : 0.0f; };
     float4 *o = out + 2 * ((long long)y * pitch8 + x);
-    o[0] = make_float4(g(y, x), g(y, x + 1), g(y, x + 2), g(y, x + 3));
-    o[1] = make_float4(g(y + 1, x), g(y + 1, x + 1), g(y + 1, x + 2), g(y + 1, x + 3));
+    o[0] = make_float4(g(y, x), g(y + 1, x), g(y, x + 1), g(y + 1, x + 1));
+    o[1] = make_float4(g(y, x + 2), g(y + 1, x + 2), g(y, x + 3), g(y + 1, x + 3));
 }
