@@ -69,8 +69,9 @@ extern "C" int qgmap_config_defaults(qgmap_config *c, int variant)
 // --------------------------------------------------------------------------------------------------------------------
 template <int KT, bool SUPER, bool DUMP>
 static void launch_inst(const qgmap_handle *h) {
-    if (h->lanes_per_belief == 4) qgmap_iter_kernel_g4<KT, SUPER, DUMP><<<h->grid, dim3(QG_TW, QG_TH + 1), 0, h->stream>>>(h->params);
-    else qgmap_iter_kernel<KT, SUPER, DUMP><<<h->grid, dim3(QG_TW, QG_TH + 1), 0, h->stream>>>(h->params);
+    const dim3 block(QG_TW, (SUPER ? QG_TH_S : QG_TH) + 1);
+    if (h->lanes_per_belief == 4) qgmap_iter_kernel_g4<KT, SUPER, DUMP><<<h->grid, block, 0, h->stream>>>(h->params);
+    else qgmap_iter_kernel<KT, SUPER, DUMP><<<h->grid, block, 0, h->stream>>>(h->params);
 }
 template <bool SUPER, bool DUMP>
 static void launch_k(const qgmap_handle *h) {
@@ -234,7 +235,8 @@ extern "C" int qgmap_create(const qgmap_config *cfg, const double *I1, const dou
         if (h->lanes_per_belief != 4) h->lanes_per_belief = 1;
     }
     const int tw = h->lanes_per_belief == 4 ? QG_CW - 1 : QG_TW - 1;
-    h->grid = dim3((N - 2 + tw - 1) / tw, std::max((out_rows + QG_TH - 1) / QG_TH, 1), h->L);
+    const int th = sup ? QG_TH_S : QG_TH;
+    h->grid = dim3((N - 2 + tw - 1) / tw, std::max((out_rows + th - 1) / th, 1), h->L);
     const size_t nblk = (size_t)h->grid.x * h->grid.y * h->grid.z;
     QG_CUDA_C(cudaMalloc(&h->partials, nblk * QG_NRED * sizeof(double)));
     QG_CUDA_C(cudaMemsetAsync(h->partials, 0, nblk * QG_NRED * sizeof(double), h->stream));

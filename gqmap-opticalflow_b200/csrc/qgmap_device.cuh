@@ -15,7 +15,9 @@
 #define QG_LMAX 10
 #define QG_KMAX 32
 #define QG_TW 32            // lanes per tile row (lane 0 = halo column)
-#define QG_TH 8             // output rows per tile (+1 halo row of threads)
+#define QG_TH 8             // output rows per tile (+1 halo row of threads), full-resolution variant
+#define QG_TH_S 4           // super-pixel variant: few, heavy beliefs -> smaller CTAs, so a straggler warp (border blocks take a
+                            // slower clamped path) holds back fewer warps at the block reduction and more CTAs fit per SM
 #define QG_NRED 4           // block-reduced scalars: energy, dalpha, sum|G_muu|, sum|G_sigu|
 
 // ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 -- two FMAs per issue slot; the iteration kernel is issue-bound,

@@ -16,6 +16,13 @@
 
 __device__ __forceinline__ float qg_clamp(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 
+// Tile rows are issued in the order 0, last, 1, 2, ...: tiles touching the top/bottom image border hold the samples that get
+// clamped to the image (the slow path of the super-pixel variant); starting them first keeps them out of the launch's tail.
+__device__ __forceinline__ int qg_tile_row() {
+    const int by = (int)blockIdx.y, last = (int)gridDim.y - 1;
+    return by == 0 ? 0 : (by == 1 ? last : by - 1);
+}
+
 __device__ __forceinline__ float qg_warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -24,10 +31,10 @@ __device__ __forceinline__ float qg_warp_sum(float v) {
 
 // Block partial sums (fp32 within a warp, fp64 across warps and blocks) of red[] = {energy, dalpha, |G_muu|, |G_sigu|}; the
 // last block to finish reduces all partials in a fixed order and advances the control block (:36,:48,:50,:69-75).
-template <bool DUMP>
+template <bool DUMP, int TH>
 __device__ __forceinline__ void qg_block_finish(const QgIterParams &p, QgCtrl *ctrl, const float (&red)[QG_NRED], int r, int j)
 {
-    __shared__ double sh_red[QG_TH + 1][QG_NRED];
+    __shared__ double sh_red[TH + 1][QG_NRED];
     __shared__ int sh_last;
 #pragma unroll
     for (int k = 0; k < QG_NRED; ++k) {
@@ -41,7 +48,7 @@ __device__ __forceinline__ void qg_block_finish(const QgIterParams &p, QgCtrl *c
     if (tid < QG_NRED) {
         double s = 0.0;
 #pragma unroll
-        for (int w = 1; w <= QG_TH; ++w) s += sh_red[w][tid];
+        for (int w = 1; w <= TH; ++w) s += sh_red[w][tid];
         p.partials[(size_t)blk * QG_NRED + tid] = s;
     }
     if (DUMP) return;
@@ -56,7 +63,7 @@ __device__ __forceinline__ void qg_block_finish(const QgIterParams &p, QgCtrl *c
     if (!sh_last) return;
     __threadfence();
     __shared__ double sh_sum[QG_LMAX * QG_NRED];
-    const int nthr = QG_TW * (QG_TH + 1), warp = tid >> 5, lane = tid & 31, nwarp = nthr / 32;
+    const int nthr = QG_TW * (TH + 1), warp = tid >> 5, lane = tid & 31, nwarp = nthr / 32;
     for (int ll = 0; ll < p.L; ++ll) {
         double acc[QG_NRED] = {0.0, 0.0, 0.0, 0.0};
         const double *pp = p.partials + (size_t)ll * nblk_l * QG_NRED;
@@ -90,7 +97,7 @@ __device__ __forceinline__ void qg_block_finish(const QgIterParams &p, QgCtrl *c
 }
 
 template <int KT, bool SUPER, bool DUMP>
-__global__ void __launch_bounds__(QG_TW *(QG_TH + 1), SUPER ? 2 : 3)
+__global__ void __launch_bounds__(QG_TW *((SUPER ? QG_TH_S : QG_TH) + 1), SUPER ? 4 : 3)
 qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
 {
     QgCtrl *ctrl = p.ctrl;
@@ -99,10 +106,11 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
     const float *__restrict__ in = p.buf[(it - 1) & 1];
     float *__restrict__ out = p.buf[it & 1];
 
+    constexpr int TH = SUPER ? QG_TH_S : QG_TH;
     const int j = threadIdx.x, r = threadIdx.y;
     const int l = blockIdx.z;
     const int n = (int)blockIdx.x * (QG_TW - 1) + j;              // global column (lane 0 = halo column n0-1)
-    const int m = p.out_r0 + (int)blockIdx.y * QG_TH + r - 1;     // global row    (warp 0 = halo row m0-1)
+    const int m = p.out_r0 + qg_tile_row() * TH + r - 1;          // global row    (warp 0 = halo row m0-1)
     const bool incol = (n >= 1) && (n <= p.N - 2);                // interior column
     const bool inrow = (m >= p.out_r0) && (m < p.out_r1);         // row this handle updates (interior by construction)
     const bool is_out = (r >= 1) && (j >= 1) && inrow && incol;
@@ -151,7 +159,7 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
     }
     // ---- endpoint-2 exchange (before the node term: the warps of a CTA then never wait for each other again until the
     //      final block reduction, and the cheap halo warp does not stall the barrier) ---------------------------------
-    __shared__ float4 sh_dn[QG_TH + 1][QG_TW];
+    __shared__ float4 sh_dn[TH + 1][QG_TW];
     sh_dn[r][j] = make_float4(gdu.du2, gdu.do2, gdv.du2, gdv.do2);          // to pixel (m+1,n)
     const float lf_du_u = __shfl_up_sync(0xffffffffu, gru.du2, 1);             // from pixel (m,n-1)
     const float lf_do_u = __shfl_up_sync(0xffffffffu, gru.do2, 1);
@@ -225,7 +233,7 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
         }
     }
 
-    qg_block_finish<DUMP>(p, ctrl, red, r, j);
+    qg_block_finish<DUMP, TH>(p, ctrl, red, r, j);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -239,7 +247,7 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
 #define QG_CW (QG_TW / QG_G)
 
 template <int KT, bool SUPER, bool DUMP>
-__global__ void __launch_bounds__(QG_TW *(QG_TH + 1), SUPER ? 2 : 3)
+__global__ void __launch_bounds__(QG_TW *((SUPER ? QG_TH_S : QG_TH) + 1), SUPER ? 4 : 3)
 qgmap_iter_kernel_g4(const __grid_constant__ QgIterParams p)
 {
     QgCtrl *ctrl = p.ctrl;
@@ -252,8 +260,9 @@ qgmap_iter_kernel_g4(const __grid_constant__ QgIterParams p)
     const int jc = j / QG_G, g = j % QG_G;                         // column group within the warp, lane within the group
     const int e = g & 1, c = g >> 1;                               // this lane's edge: e 0=down 1=right, layer c 0=u 1=v
     const int l = blockIdx.z;
+    constexpr int TH = SUPER ? QG_TH_S : QG_TH;
     const int n = (int)blockIdx.x * (QG_CW - 1) + jc;              // global column (group 0 = halo column n0-1)
-    const int m = p.out_r0 + (int)blockIdx.y * QG_TH + r - 1;      // global row    (warp 0 = halo row m0-1)
+    const int m = p.out_r0 + qg_tile_row() * TH + r - 1;           // global row    (warp 0 = halo row m0-1)
     const bool incol = (n >= 1) && (n <= p.N - 2);
     const bool inrow = (m >= p.out_r0) && (m < p.out_r1);
     const bool is_out = (r >= 1) && (jc >= 1) && inrow && incol;
@@ -279,7 +288,7 @@ qgmap_iter_kernel_g4(const __grid_constant__ QgIterParams p)
         ge = qg_edge<KT>(p.tab, p.K, a, __ldg(mu + idx), __ldg(mu + inb), __ldg(sg + idx), __ldg(sg + inb), rouq, p.lambdas, p.epsn, T);
     }
     // ---- endpoint-2 exchange: down edges through shared memory to the row below, right edges by shuffle to the next group
-    __shared__ float sh_dn[QG_TH + 1][QG_CW][4];
+    __shared__ float sh_dn[TH + 1][QG_CW][4];
     if (e == 0) { sh_dn[r][jc][2 * c] = ge.du2; sh_dn[r][jc][2 * c + 1] = ge.do2; }
     const float lf_du = __shfl_up_sync(0xffffffffu, ge.du2, QG_G);            // lanes e==1: right edge of pixel (m,n-1), same layer
     const float lf_do = __shfl_up_sync(0xffffffffu, ge.do2, QG_G);
@@ -364,5 +373,5 @@ qgmap_iter_kernel_g4(const __grid_constant__ QgIterParams p)
             }
         }
     }
-    qg_block_finish<DUMP>(p, ctrl, red, r, j);
+    qg_block_finish<DUMP, TH>(p, ctrl, red, r, j);
 }
