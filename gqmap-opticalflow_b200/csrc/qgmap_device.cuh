@@ -353,6 +353,35 @@ __device__ __forceinline__ QgMoments qg_quadrature(const QgTables &tab, int Krt,
     return m;
 }
 
+// Flat split of the K*K quadrature points over `nlanes` lanes (k = lane, lane+nlanes, ...): better balance than whole rows
+// when K is small against the lane count (K=5 over 4 lanes: 7,6,6,6 points instead of 10,5,5,5).  Used by the super-pixel
+// variant, whose ~300-instruction node sample dwarfs the per-point table look-ups.
+template <int KT, class F>
+__device__ __forceinline__ QgMoments qg_quadrature_flat(const QgTables &tab, int Krt, float u1, float u2, float o1, float o2,
+                                                        const QgSpectral &sp, float scale, F pot, int lane, int nlanes)
+{
+    const float sqrt2 = 1.4142135623730951f;
+    const int K = KT > 0 ? KT : Krt;
+    const float2 aI = make_float2(sqrt2 * o1 * sp.s, sqrt2 * o2 * sp.t), aJ = make_float2(sqrt2 * o1 * sp.t, sqrt2 * o2 * sp.s);
+    const float2 u12 = make_float2(u1, u2);
+    QgMoments m = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int k = lane; k < K * K; k += nlanes) {
+        const int c = k / K, r = k - c * K;                        // reference order k = r + K*c (:9)
+        const float xc = tab.X[c], xr = tab.X[r];
+        const float f = pot(qg_fma2(aI, qg_bc(xc), qg_fma2(aJ, qg_bc(xr), u12)));
+        const float wf = tab.W[c] * tab.W[r] * f;
+        m.E += wf;
+        m.MI = fmaf(wf, xc, m.MI);
+        m.MJ = fmaf(wf, xr, m.MJ);
+        m.MII = fmaf(wf * xc, xc, m.MII);
+        m.MJJ = fmaf(wf * xr, xr, m.MJJ);
+        m.MB = fmaf(wf * xc, xr, m.MB);
+    }
+    m.E *= scale; m.MI *= scale; m.MJ *= scale; m.MII *= scale; m.MJJ *= scale; m.MB *= scale;
+    return m;
+}
+
 // Edge quadrature (:118-146): the potential depends on x1-x2 only, which is affine in (XI,XJ):
 // x1-x2 = (u1-u2) + A*XI + B*XJ.  One FMA + one MUFU per point.
 template <int KT>

@@ -334,7 +334,7 @@ qgmap_iter_kernel_g4(const __grid_constant__ QgIterParams p)
                 I1b[di * 4 + 0] = v.x; I1b[di * 4 + 1] = v.y; I1b[di * 4 + 2] = v.z; I1b[di * 4 + 3] = v.w;
             }
             const int lastx = p.No - 2, lasty = p.Mo - 2, m4 = 4 * m, n4 = 4 * n;
-            mo = qg_quadrature<KT>(p.tab, p.K, muu, muv, sigu, sigv, sp, -p.lambdad, [&](float2 x) {
+            mo = qg_quadrature_flat<KT>(p.tab, p.K, muu, muv, sigu, sigv, sp, -p.lambdad, [&](float2 x) {
                 return qg_super_sample(p.VV8, p.pitchV, m4, n4, lastx, lasty, x, I1b, p.epsn);
             }, g, QG_G);
         } else {
