@@ -1,0 +1,84 @@
+"""Edge cases of the hot path on the GPU against the oracle: smallest grids, ragged sizes, extreme L and K, samples clamped far
+outside the image, degenerate clamp ranges (Venus/Teddy/Cones have minv == maxv == 0), alpha exactly 0."""
+import numpy as np
+import pytest
+
+from conftest import make_problem, options_from_cfg, state_dict
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True, params=["1", "4"], ids=["lanes1", "lanes4"])
+def lanes_per_belief(request, monkeypatch):
+    monkeypatch.setenv("QGMAP_LANES", request.param)
+    return request.param
+
+
+def _check(pkg, O, cfg, I1, I2, st, variant, T=0.0, rtol=4e-4):
+    VV = O.get_vv(I2)
+    g = O.gradients(cfg, I1, VV, st, assemble=True)
+    with pkg.Solver(options_from_cfg(cfg, T=T), I1, I2, variant=variant) as s:
+        s.set_state(state_dict(st), T=T)
+        d = s.debug_gradients()
+        r = s.step(1)
+    ref = st.copy()
+    _, _, _, E, dm, ds = O.run(cfg, I1, VV, ref, 1, 10 ** 6, 1)
+    # absolute floor: fp32 evaluation of sums that cancel exactly in exact arithmetic (e.g. the sigma gradient is identically 0
+    # for K=2, where XI^2+XJ^2-1 = 0 at every point) leaves noise at 1e-7 of the potentials' magnitude
+    floor = 0.05 * max(np.abs(g["dmuu"]).max(), np.abs(g["dsigmau"]).max(), 1e-3)
+    for name, want in (("G_muu", g["dmuu"]), ("G_muv", g["dmuv"]), ("G_sigu", g["dsigmau"]), ("G_sigv", g["dsigmav"]),
+                       ("dpn", g["dpn"]), ("drou", g["drou"])):
+        a, b = d[name][1:-1, 1:-1], want[1:-1, 1:-1]
+        assert np.abs(a - b).max() <= rtol * max(np.abs(b).max(), floor), name
+    assert abs(r["Energy"][0] / E[0] - 1) < 1e-5 and abs(r["ptdmu"][0] / dm[0] - 1) < 1e-3
+
+
+@pytest.mark.parametrize("variant,shape", [("full", (4, 4)), ("full", (5, 9)), ("full", (33, 34)), ("full", (8, 97)),
+                                           ("super", (12, 12)), ("super", (16, 36)), ("super", (132, 20))])
+def test_small_and_ragged_grids(pkg, O, variant, shape):
+    sup = variant == "super"
+    cfg, I1, I2, st = make_problem(O, shape[0], shape[1], 2, 3, super=sup, seed=41, small_sigma=True)
+    _check(pkg, O, cfg, I1, I2, st, variant)
+
+
+@pytest.mark.parametrize("L,K", [(10, 3), (1, 2), (2, 13), (1, 32)])
+def test_extreme_L_and_K(pkg, O, L, K):
+    cfg, I1, I2, st = make_problem(O, 20, 24, L, K, seed=43, small_sigma=True)
+    _check(pkg, O, cfg, I1, I2, st, "full", rtol=6e-4)
+
+
+@pytest.mark.parametrize("variant", ["full", "super"])
+def test_samples_clamped_far_outside_image(pkg, O, variant):
+    """Teddy/Cones-like range (|u| up to 55 px) on a tiny frame: most quadrature points clamp to the image border (:157-161)."""
+    sup = variant == "super"
+    shape = (40, 48) if not sup else (64, 80)
+    cfg, I1, I2, st = make_problem(O, shape[0], shape[1], 2, 5, super=sup, seed=47, minu=-55.0, maxu=3.0, minv=-30.0, maxv=30.0)
+    _check(pkg, O, cfg, I1, I2, st, variant)
+
+
+def test_degenerate_clamp_range_pins_the_mean(pkg, O):
+    """minv == maxv == 0 (Venus, Teddy, Cones ground truth): mu_v stays 0, sigma_v starts at rand (:20,:22)."""
+    cfg, I1, I2, st = make_problem(O, 24, 28, 2, 3, seed=49, minv=0.0, maxv=0.0)
+    assert np.all(st.muv == 0)
+    with pkg.Solver(options_from_cfg(cfg), I1, I2) as s:
+        s.set_state(state_dict(st))
+        s.step(5)
+        got = s.get_state()
+    assert np.all(got["muv"] == 0) and np.all(got["sigmav"][1:-1, 1:-1] >= np.float32(0.01))     # border beliefs keep their init (:41-46)
+    _check(pkg, O, cfg, I1, I2, st, "full")
+
+
+def test_zero_weight_component(pkg, O):
+    """alpha_l == 0 exactly (reachable with projsplx): the reference skips the accumulators (`if a~=0`, :98); every
+    gradient of that component is 0 either way and its energy term vanishes."""
+    cfg, I1, I2, st = make_problem(O, 20, 24, 3, 3, seed=51, small_sigma=True)
+    st.alpha[:] = [0.6, 0.0, 0.4]
+    VV = O.get_vv(I2)
+    g = O.gradients(cfg, I1, VV, st, assemble=True)
+    with pkg.Solver(options_from_cfg(cfg), I1, I2) as s:
+        s.set_state(state_dict(st), alpha=st.alpha)
+        d = s.debug_gradients()
+    for name in ("G_muu", "G_sigv", "dpn", "e_px"):
+        assert np.all(d[name][:, :, 1] == 0)
+    assert np.all(g["dmuu"][1:-1, 1:-1, 1] == 0)
+    assert np.abs(d["G_muu"][1:-1, 1:-1, 0] - g["dmuu"][1:-1, 1:-1, 0]).max() < 4e-4 * np.abs(g["dmuu"]).max()
