@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqgmap.so")
+# QGMAP_LIB_PATH: development aid for A/B timing of two builds of the same library (never a fallback: the file must exist)
+LIB_PATH = os.environ.get("QGMAP_LIB_PATH") or os.path.join(_HERE, "libqgmap.so")
 
 QGMAP_LMAX = 10
 QGMAP_KMAX = 32

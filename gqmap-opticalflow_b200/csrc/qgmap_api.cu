@@ -69,7 +69,7 @@ extern "C" int qgmap_config_defaults(qgmap_config *c, int variant)
 // --------------------------------------------------------------------------------------------------------------------
 template <int KT, bool SUPER, bool DUMP>
 static void launch_inst(const qgmap_handle *h) {
-    const dim3 block(QG_TW, (SUPER ? QG_TH_S : QG_TH) + 1);
+    const dim3 block(QG_TW, QgTile<KT, SUPER>::TH + 1);
     if (h->lanes_per_belief == 4) qgmap_iter_kernel_g4<KT, SUPER, DUMP><<<h->grid, block, 0, h->stream>>>(h->params);
     else qgmap_iter_kernel<KT, SUPER, DUMP><<<h->grid, block, 0, h->stream>>>(h->params);
 }
@@ -165,6 +165,8 @@ extern "C" int qgmap_create(const qgmap_config *cfg, const double *I1, const dou
     if (cfg->L < 1 || cfg->L > QGMAP_LMAX) QG_FAIL((qgmap_handle *)nullptr, QGMAP_ERR_ARG, "L=%d out of range 1..%d", cfg->L, QGMAP_LMAX);
     if (cfg->K < 1 || cfg->K > QGMAP_KMAX) QG_FAIL((qgmap_handle *)nullptr, QGMAP_ERR_ARG, "K=%d out of range 1..%d", cfg->K, QGMAP_KMAX);
     if (Mo < 4 || No < 4) QG_FAIL((qgmap_handle *)nullptr, QGMAP_ERR_ARG, "image %dx%d too small (bicubic needs >=4x4)", Mo, No);
+    if ((long long)(Mo + 2) * ((No + 3) / 4 * 4 + 4) >= (1LL << 31))
+        QG_FAIL((qgmap_handle *)nullptr, QGMAP_ERR_ARG, "image %dx%d too large (gather entries are indexed with 32 bits)", Mo, No);
     if (sup && (Mo % 4 || No % 4)) QG_FAIL((qgmap_handle *)nullptr, QGMAP_ERR_ARG, "super-pixel variant needs Mo,No divisible by 4 (got %dx%d)", Mo, No);
     const int M = sup ? Mo / 4 : Mo, N = sup ? No / 4 : No;
     if (M < 3 || N < 3) QG_FAIL((qgmap_handle *)nullptr, QGMAP_ERR_ARG, "belief grid %dx%d has no interior", M, N);
@@ -235,7 +237,7 @@ extern "C" int qgmap_create(const qgmap_config *cfg, const double *I1, const dou
         if (h->lanes_per_belief != 4) h->lanes_per_belief = 1;
     }
     const int tw = h->lanes_per_belief == 4 ? QG_CW - 1 : QG_TW - 1;
-    const int th = sup ? QG_TH_S : QG_TH;
+    const int th = qg_tile_rows(h->K, sup);
     h->grid = dim3((N - 2 + tw - 1) / tw, std::max((out_rows + th - 1) / th, 1), h->L);
     const size_t nblk = (size_t)h->grid.x * h->grid.y * h->grid.z;
     QG_CUDA_C(cudaMalloc(&h->partials, nblk * QG_NRED * sizeof(double)));

@@ -15,9 +15,19 @@
 #define QG_LMAX 10
 #define QG_KMAX 32
 #define QG_TW 32            // lanes per tile row (lane 0 = halo column)
-#define QG_TH 8             // output rows per tile (+1 halo row of threads), full-resolution variant
-#define QG_TH_S 4           // super-pixel variant: few, heavy beliefs -> smaller CTAs, so a straggler warp (border blocks take a
-                            // slower clamped path) holds back fewer warps at the block reduction and more CTAs fit per SM
+// Tile shape per kernel instantiation: a CTA is QG_TW lanes x (TH+1) warps (warp 0 = halo row), compiled for MINB resident CTAs
+// per SM.  Measured on B200 (profiles/r01_tile_ab.txt): small quadrature orders (K <= 5) are latency-bound and gain from 4 CTAs
+// of 8 warps at 64 registers (+4% K=5, +12% K=3); K >= 7 is FMA-pipe/issue-bound and keeps 3 CTAs of 9 warps at 72 registers.
+// The super-pixel variant has few, heavy beliefs: smaller CTAs, so a straggler warp (border blocks take a slower clamped path)
+// holds back fewer warps at the block reduction.
+template <int KT, bool SUPER> struct QgTile {
+    static constexpr int TH = SUPER ? 4 : ((KT > 0 && KT <= 5) ? 7 : 8);
+    static constexpr int MINB = SUPER ? 4 : ((KT > 0 && KT <= 5) ? 4 : 3);
+};
+__host__ __device__ constexpr int qg_tile_rows(int K, bool super) {      // host mirror of QgTile<K,SUPER>::TH (template K set)
+    return super ? 4 : ((K == 3 || K == 5) ? 7 : 8);
+}
+#define QG_TH_MAX 8
 #define QG_NRED 4           // block-reduced scalars: energy, dalpha, sum|G_muu|, sum|G_sigu|
 
 // ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 -- two FMAs per issue slot; the iteration kernel is issue-bound,

@@ -6,10 +6,10 @@
 // (:36,:48,:69-70).  The last block to finish reduces the partials in a fixed order and advances the device-resident
 // control block (step counter, alpha softmax / projsplx update :50,:78-86, temperature anneal S:72, stop test :75).
 //
-// Tiling: a CTA is 32 lanes x (QG_TH+1) warps.  Warp 0 is the halo row above the tile and lane 0 the halo column left
+// Tiling: a CTA is 32 lanes x (TH+1) warps (TH = QgTile<K,SUPER>::TH).  Warp 0 is the halo row above the tile and lane 0 the halo column left
 // of it: they evaluate only the edge whose endpoint-2 gradient an output pixel needs (Jacobi semantics: every gradient
 // uses the OLD state, written state goes to the other ping-pong buffer).  Down-edge endpoint-2 gradients travel through
-// shared memory to the warp below, right-edge ones through a warp shuffle to the next lane.  Output tile = 31 x QG_TH.
+// shared memory to the warp below, right-edge ones through a warp shuffle to the next lane.  Output tile = 31 x TH.
 #pragma once
 #include "qgmap_device.cuh"
 #include "qgmap_advance.cuh"
@@ -97,7 +97,7 @@ __device__ __forceinline__ void qg_block_finish(const QgIterParams &p, QgCtrl *c
 }
 
 template <int KT, bool SUPER, bool DUMP>
-__global__ void __launch_bounds__(QG_TW *((SUPER ? QG_TH_S : QG_TH) + 1), SUPER ? 4 : 3)
+__global__ void __launch_bounds__(QG_TW *(QgTile<KT, SUPER>::TH + 1), QgTile<KT, SUPER>::MINB)
 qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
 {
     QgCtrl *ctrl = p.ctrl;
@@ -106,7 +106,7 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
     const float *__restrict__ in = p.buf[(it - 1) & 1];
     float *__restrict__ out = p.buf[it & 1];
 
-    constexpr int TH = SUPER ? QG_TH_S : QG_TH;
+    constexpr int TH = QgTile<KT, SUPER>::TH;
     const int j = threadIdx.x, r = threadIdx.y;
     const int l = blockIdx.z;
     const int n = (int)blockIdx.x * (QG_TW - 1) + j;              // global column (lane 0 = halo column n0-1)
@@ -242,12 +242,12 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
 // components): lane g of a group evaluates edge quadrature q = g (q = e + 2c: down-u, right-u, down-v, right-v -- the four
 // are perfectly balanced) and the XJ rows r = g, g+4, ... of the node quadrature; the six node moments are combined with
 // two xor-shuffles, the edge gradients with one or two (north_star: "warp-shuffle reductions of the gradients").
-// A warp covers 8 columns (column group 0 = halo column); tile = 7 x QG_TH outputs.
+// A warp covers 8 columns (column group 0 = halo column); tile = 7 x TH outputs.
 #define QG_G 4
 #define QG_CW (QG_TW / QG_G)
 
 template <int KT, bool SUPER, bool DUMP>
-__global__ void __launch_bounds__(QG_TW *((SUPER ? QG_TH_S : QG_TH) + 1), SUPER ? 4 : 3)
+__global__ void __launch_bounds__(QG_TW *(QgTile<KT, SUPER>::TH + 1), QgTile<KT, SUPER>::MINB)
 qgmap_iter_kernel_g4(const __grid_constant__ QgIterParams p)
 {
     QgCtrl *ctrl = p.ctrl;
@@ -260,7 +260,7 @@ qgmap_iter_kernel_g4(const __grid_constant__ QgIterParams p)
     const int jc = j / QG_G, g = j % QG_G;                         // column group within the warp, lane within the group
     const int e = g & 1, c = g >> 1;                               // this lane's edge: e 0=down 1=right, layer c 0=u 1=v
     const int l = blockIdx.z;
-    constexpr int TH = SUPER ? QG_TH_S : QG_TH;
+    constexpr int TH = QgTile<KT, SUPER>::TH;
     const int n = (int)blockIdx.x * (QG_CW - 1) + jc;              // global column (group 0 = halo column n0-1)
     const int m = p.out_r0 + qg_tile_row() * TH + r - 1;           // global row    (warp 0 = halo row m0-1)
     const bool incol = (n >= 1) && (n <= p.N - 2);
