@@ -234,8 +234,8 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "pixel-iter/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "its_per_call": its_e2e, "calls_per_step": len(items), "steps": args.e2e_steps, "gpu_launches": int(e2e_launches),
                 "api": "gqmap_gpu_mixture(options,I1,I2) -> qgmap_solve (C ABI), pinned host buffers in, host arrays out, "
-                       "monitoring (MAP/logP) at it=1 and every 300 as the reference; each call starts from the random init (its "
-                       "iterations are the slow, incoherent first phase of the ascent)"},
+                       "monitoring (MAP/logP) at it=1 and every 300 as the reference; each call is a whole solve from the random init with "
+                       "options.its = %d (the reference drivers use 30000, optical_flow.m:17)" % its_e2e},
         "roofline": {"bound": "fp32", "achieved": ach_tf, "peak": fp32_meas, "unit": "TFLOP/s", "frac": ach_tf / fp32_meas,
                      "peak_source": "FFMA micro-benchmark measured live on this GPU (qgmap_fp32_peak); nominal 148x128x2x1.965GHz = %.1f" % fp32_nominal,
                      "frac_of_nominal": ach_tf / fp32_nominal,
@@ -272,8 +272,9 @@ def run_band4k(args):
         rb, re = pkg.dist.band_rows(M, rank, world)
         opts.update(row_begin=rb, row_end=re)
     s = pkg.Solver(opts, I1, I2)
+    transport = "none"
     if world > 1:
-        pkg.dist.connect_band(s, dist, device=torch.device("cuda", local))
+        transport = pkg.dist.connect_band(s, dist, device=torch.device("cuda", local), transport=args.band_transport)
     s.init_state(seed=4321)
     iters = args.iters
 
@@ -310,7 +311,9 @@ def run_band4k(args):
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "one synthetic %dx%d frame pair, L=3, K=5, gqmap_gpu_mixture path, %d row band(s), 1-row halo exchange + "
-                                   "4L-double all-reduce per iteration over NCCL; %d iterations per step after %d burn-in" % (N, M, world, iters, args.burnin),
+                                   "4L-double global sum per iteration, transport %s (p2p = libqgmap's publish kernel over NVLink peer memory, "
+                                   "nccl = send/recv + all-reduce); %d iterations per step after %d burn-in" % (N, M, world, transport, iters, args.burnin),
+                       "transport": transport,
                        "iters_per_step": iters, "parallelism": "row bands x%d" % world,
                        "l2": "state 2 x %.0f MB + gather layout %.0f MB exceed the 126 MB L2" % (M * N * 9 * L * 4 / 1e6 / world, (M + 2) * N * 32 / 1e6)},
             "clocks": clocks, "gpu_launches": int(launches),
@@ -401,11 +404,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--iters", type=int, default=200, help="ascent iterations per frame pair per step (device-resident leg)")
     ap.add_argument("--burnin", type=int, default=3000, help="untimed iterations per pair before the warm-up steps")
-    ap.add_argument("--e2e-its", type=int, default=5000, help="options.its of each end-to-end gqmap_gpu_mixture call")
+    ap.add_argument("--e2e-its", type=int, default=30000, help="options.its of each end-to-end gqmap_gpu_mixture call (optical_flow.m:17: 30000)")
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--ref-iters", type=int, default=1, help="reference arm: iterations per pair per step")
     ap.add_argument("--workload", default="middlebury8", choices=["middlebury8", "band4k"],
                     help="middlebury8 = BASELINE configs[1] (default, independent pairs sharded by rank); band4k = configs[3] (one 4K pair in row bands)")
+    ap.add_argument("--band-transport", default=None, choices=["p2p", "nccl"], help="band4k: halo/sum transport (default p2p)")
     ap.add_argument("--band-rows", type=int, default=2160)
     ap.add_argument("--band-cols", type=int, default=3840)
     ap.add_argument("--ref-pairs", type=int, default=8, help="reference arm: how many of the 8 pairs form the bounded sample")

@@ -7,6 +7,6 @@ The directory name carries a hyphen (it mirrors the reference repo name); import
 from . import _lib                                     # noqa: F401  (raises if libqgmap.so is absent)
 from ._lib import QgmapError, QgmapConfig, LIB_PATH    # noqa: F401
 from .host import (gqmap_gpu_mixture, gqmap_gpuSuper_mix_entropy, get_map_mex, flowToColor_mex,   # noqa: F401
-                   GaussHermite_2, projsplx, Solver, make_config, last_solve_stats, batch_step, fp32_peak, BandGroup)
-from .frames import readFlowFile, rgb2gray, synthetic_pair, middlebury_shapes                     # noqa: F401
+                   GaussHermite_2, projsplx, imwrite, Solver, make_config, last_solve_stats, batch_step, fp32_peak, BandGroup)
+from .frames import readFlowFile, writeFlowFile, save_results, rgb2gray, synthetic_pair, middlebury_shapes                     # noqa: F401
 from . import dist                                    # noqa: F401,E402

@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("QGMAP_LIB_PATH") or os.path.join(_HERE, "libqgmap.so")
 
 QGMAP_LMAX = 10
+QGMAP_P2P_BLOB_BYTES = 512
 QGMAP_KMAX = 32
 VARIANT_FULL, VARIANT_SUPER = 0, 1
 ALPHA_SOFTMAX, ALPHA_PROJSPLX = 0, 1
@@ -67,11 +68,17 @@ SIGNATURES = {
     "qgmap_last_solve_stats": (C.c_int, [C.POINTER(C.c_longlong), C.POINTER(C.c_float)]),
     "qgmap_find_map": (C.c_int, [_DP] * 5 + [C.c_int, C.c_int, C.c_int, _DP, C.c_int]),
     "qgmap_flow_to_color": (C.c_int, [_DP, C.c_int, C.c_int, C.c_double, _U8P, _DP, _DP, _U8P]),
+    "qgmap_write_png": (C.c_int, [C.c_char_p, _U8P, C.c_int, C.c_int]),
+    "qgmap_solve_set_dump_dir": (C.c_int, [C.c_char_p]),
+    "qgmap_read_flo": (C.c_int, [C.c_char_p, _IP, _IP, _DP]),
+    "qgmap_write_flo": (C.c_int, [C.c_char_p, _DP, C.c_int, C.c_int]),
     "qgmap_gauss_hermite": (C.c_int, [C.c_int, _DP, _DP]),
     "qgmap_projsplx": (C.c_int, [_DP, C.c_int, _DP]),
     "qgmap_debug_gradients": (C.c_int, [C.c_void_p] + [_DP] * 8),
     "qgmap_band_unique_id": (C.c_int, [C.c_void_p]),
     "qgmap_band_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "qgmap_band_p2p_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "qgmap_band_p2p_connect": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "qgmap_group_create": (C.c_int, [C.POINTER(QgmapConfig), _DP, _DP, C.c_int, C.c_int, C.c_int, _IP, C.POINTER(C.c_void_p)]),
     "qgmap_group_destroy": (C.c_int, [C.c_void_p]),
     "qgmap_group_dims": (C.c_int, [C.c_void_p, _IP, _IP, _IP, _IP]),

@@ -111,6 +111,7 @@ static void free_handle(qgmap_handle *h)
     if (!h) return;
     if (h->device >= 0) cudaSetDevice(h->device);
     qgmap_band_release(h);
+    qgmap_p2p_release(h);
     if (h->graph) cudaGraphExecDestroy(h->graph);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -453,7 +454,10 @@ extern "C" int qgmap_step_begin(qgmap_handle *h, int n, int its)
     long long launches = 0;
     QG_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     int left = n;
-    if (h->nranks > 1) {
+    if (h->nranks > 1 && h->p2p) {                       // row band, exchange by our own kernel over peer memory (qgmap_p2p.cu)
+        qgmap_p2p_begin_step(h);
+        for (; left > 0; --left) { if ((rc = qgmap_p2p_iteration(h, &launches)) != QGMAP_OK) return rc; ++launches; }
+    } else if (h->nranks > 1) {                          // row band over NCCL (qgmap_band.cu)
         for (; left > 0; --left) { if ((rc = qgmap_band_iteration(h, &launches)) != QGMAP_OK) return rc; ++launches; }
     } else {
         if (left >= kGraphLen && (rc = build_graph(h)) != QGMAP_OK) return rc;
@@ -478,6 +482,8 @@ extern "C" int qgmap_step_end(qgmap_handle *h, double *energy, double *ptdmu, do
     QG_CUDA(h, cudaStreamSynchronize(h->stream));
     cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
     cudaGetLastError();
+    if (h->ctrl_host->comm_error)
+        QG_FAIL(h, QGMAP_ERR_COMM, "band exchange timed out at iteration %d: a peer rank did not publish its boundary rows", h->ctrl_host->it);
     const int done = h->ctrl_host->it - h->it0;
     if (n_done) *n_done = done;
     if (stopped) *stopped = h->ctrl_host->stop;
@@ -774,6 +780,37 @@ extern "C" int qgmap_find_map(const double *alpha, const double *mu_u, const dou
 }
 
 // ---- one-call solver == gqmap_gpu_mixture(options,I1,I2) -----------------------------------------------------------------
+// options.dir (gqmap_gpu_mixture.m:62): colour-coded MAP flow of the monitored iterations as <dir>/<it>.png
+static thread_local std::string g_dump_dir;
+extern "C" int qgmap_solve_set_dump_dir(const char *dir)
+{
+    g_dump_dir = dir ? dir : "";
+    return QGMAP_OK;
+}
+static int dump_map_png(qgmap_handle *h, int it)
+{
+    const int M = h->M, N = h->N;
+    std::vector<double> map((size_t)M * N * 2);
+    QG_CUDA(h, cudaMemcpyAsync(map.data(), h->d_map, map.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    QG_CUDA(h, cudaStreamSynchronize(h->stream));
+    int Mi = M, Ni = N;
+    std::vector<double> flow;
+    if (h->cfg.variant == QGMAP_VARIANT_SUPER) {                 // flow = repelem(map,4,4); flc = flowToColor_mex(flow(5:end-4,5:end-4,:)) (S:58-59)
+        Mi = 4 * M - 8; Ni = 4 * N - 8;
+        if (Mi < 1 || Ni < 1) return QGMAP_OK;
+        flow.resize((size_t)Mi * Ni * 2);
+        for (int c = 0; c < 2; ++c)
+            for (int n = 0; n < Ni; ++n)
+                for (int m = 0; m < Mi; ++m)
+                    flow[(size_t)m + (size_t)Mi * n + (size_t)Mi * Ni * c] = map[(size_t)((m + 4) / 4) + (size_t)M * ((n + 4) / 4) + (size_t)M * N * c];
+    } else flow.swap(map);
+    std::vector<uint8_t> img((size_t)Mi * Ni * 3);
+    int rc = qgmap_flow_to_color(flow.data(), Mi, Ni, -1.0, img.data(), nullptr, nullptr, nullptr);
+    if (rc == QGMAP_OK) rc = qgmap_write_png((g_dump_dir + "/" + std::to_string(it) + ".png").c_str(), img.data(), Mi, Ni);
+    if (rc != QGMAP_OK) QG_FAIL(h, rc, "could not write %s/%d.png (options.dir must exist)", g_dump_dir.c_str(), it);
+    return QGMAP_OK;
+}
+
 extern "C" int qgmap_solve(const qgmap_config *cfg, const double *I1, const double *I2, int Mo, int No, int its,
                            const double *const *init, uint64_t seed, const double *tflow, const uint8_t *unknown,
                            double *mu, double *sigma, double *alpha, double *AEPE, double *Energy, double *logP,
@@ -811,6 +848,7 @@ extern "C" int qgmap_solve(const qgmap_config *cfg, const double *I1, const doub
         const int last = it - 1;                                                      // last executed iteration
         if (done > 0 && (last == 1 || last % every == 0)) {                           // :52-68
             if ((rc = map_device(h)) != QGMAP_OK) return bail(rc);
+            if (!g_dump_dir.empty() && (rc = dump_map_png(h, last)) != QGMAP_OK) return bail(rc);    // :59-62
             if (tflow && AEPE && (rc = aepe_device(h, h->d_map, &AEPE[last - 1])) != QGMAP_OK) return bail(rc);
             if (logP && (rc = logp_device(h, h->d_map, &logP[last - 1])) != QGMAP_OK) return bail(rc);
             launches += 1 + (tflow && AEPE ? 1 : 0) + (logP ? 1 : 0);

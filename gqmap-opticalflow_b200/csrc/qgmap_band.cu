@@ -22,6 +22,7 @@
 #include <nccl.h>
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -172,6 +173,7 @@ struct qgmap_group {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int M = 0, N = 0, L = 0;
     float last_ms = 0.f;
+    bool p2p = false;                             // bands on distinct GPUs: publish-kernel exchange (qgmap_p2p.cu)
     std::string err;
 };
 
@@ -249,6 +251,19 @@ extern "C" int qgmap_group_create(const qgmap_config *cfg, const double *I1, con
             cudaMemcpy((void *)g->d_sumptrs[b], ptrs.data(), nbands * sizeof(double *), cudaMemcpyHostToDevice) != cudaSuccess)
             return bail(QGMAP_ERR_CUDA);
     }
+    // every band on its own GPU: exchange through the publish kernel over peer memory (qgmap_p2p.cu) -- two launches per band
+    // and iteration, no events.  Bands sharing a GPU keep the event-ordered copies below: a kernel that waits for another
+    // kernel's flag must not rely on the two being co-scheduled on one device.
+    bool distinct = nbands > 1;
+    for (int a = 0; a < nbands && distinct; ++a)
+        for (int b = a + 1; b < nbands; ++b) if (g->bands[a]->device == g->bands[b]->device) distinct = false;
+    if (const char *env = getenv("QGMAP_GROUP_TRANSPORT")) { if (!strcmp(env, "events")) distinct = false; else if (!strcmp(env, "p2p") && nbands > 1) distinct = true; }
+    if (distinct && nbands <= QGMAP_P2P_RANKS_MAX) {
+        std::vector<char> blobs((size_t)nbands * QGMAP_P2P_BLOB_BYTES);
+        for (int b = 0; b < nbands; ++b) { int rc = qgmap_band_p2p_export(g->bands[b], blobs.data() + (size_t)b * QGMAP_P2P_BLOB_BYTES); if (rc) return bail(rc); }
+        for (int b = 0; b < nbands; ++b) { int rc = qgmap_band_p2p_connect(g->bands[b], b, nbands, blobs.data()); if (rc) return bail(rc); }
+        g->p2p = true;
+    }
     cudaSetDevice(g->bands[0]->device);
     if (cudaEventCreate(&g->ev0) != cudaSuccess || cudaEventCreate(&g->ev1) != cudaSuccess) return bail(QGMAP_ERR_CUDA);
     *out = g;
@@ -311,7 +326,18 @@ extern "C" int qgmap_group_step(qgmap_group *g, int n, int its, double *energy, 
     QGB_CUDA(h0, cudaSetDevice(h0->device));
     QGB_CUDA(h0, cudaEventRecord(g->ev0, h0->stream));
     for (int b = 1; b < nb; ++b) { cudaSetDevice(g->bands[b]->device); QGB_CUDA(g->bands[b], cudaStreamWaitEvent(g->bands[b]->stream, g->ev0, 0)); }
-    for (int k = 0; k < n; ++k) {
+    if (g->p2p) {
+        for (qgmap_handle *h : g->bands) qgmap_p2p_begin_step(h);
+        for (int k = 0; k < n; ++k)
+            for (int b = 0; b < nb; ++b) {
+                qgmap_handle *h = g->bands[b];
+                long long nl = 0;
+                QGB_CUDA(h, cudaSetDevice(h->device));
+                int rc = qgmap_p2p_iteration(h, &nl);
+                if (rc) { g->err = h->err; return rc; }
+            }
+    }
+    for (int k = 0; k < (g->p2p ? 0 : n); ++k) {
         const int wbuf = (it_start + k) & 1;                               // buffer written by this iteration
         for (int b = 0; b < nb; ++b) {                                     // 1. iteration kernels (need neighbours' halos: ev_adv waits below)
             qgmap_handle *h = g->bands[b];

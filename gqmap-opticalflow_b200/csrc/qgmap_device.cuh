@@ -96,6 +96,7 @@ struct QgCtrl {
     double alpha[QG_LMAX];  // mixture weights
     double dalpha[QG_LMAX]; // last reduced d(alpha) (:36)
     double sums[QG_LMAX * QG_NRED];   // band mode: this rank's per-component partial sums awaiting all-reduce
+    int comm_error;         // band p2p mode: a peer did not publish its iteration in time (the run was stopped)
 };
 
 struct QgIterParams {

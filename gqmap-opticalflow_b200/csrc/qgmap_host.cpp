@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -146,6 +147,117 @@ extern "C" int qgmap_flow_to_color(const double *flow, int M, int N, double max_
         }
     }
     return QGMAP_OK;
+}
+
+// ---- PNG (imwrite replacement, gqmap_gpu_mixture.m:62): 8-bit RGB, filter 0, zlib stream of stored deflate blocks ----
+static uint32_t crc32_update(uint32_t c, const uint8_t *p, size_t n)
+{
+    static uint32_t table[256];
+    static bool init = false;
+    if (!init) {
+        for (uint32_t i = 0; i < 256; ++i) {
+            uint32_t v = i;
+            for (int k = 0; k < 8; ++k) v = (v & 1) ? 0xEDB88320u ^ (v >> 1) : v >> 1;
+            table[i] = v;
+        }
+        init = true;
+    }
+    for (size_t i = 0; i < n; ++i) c = table[(c ^ p[i]) & 0xFF] ^ (c >> 8);
+    return c;
+}
+static void put_be32(std::vector<uint8_t> &v, uint32_t x) { for (int s = 24; s >= 0; s -= 8) v.push_back((uint8_t)(x >> s)); }
+static void png_chunk(std::vector<uint8_t> &out, const char *type, const std::vector<uint8_t> &data)
+{
+    put_be32(out, (uint32_t)data.size());
+    std::vector<uint8_t> td(type, type + 4);
+    td.insert(td.end(), data.begin(), data.end());
+    out.insert(out.end(), td.begin(), td.end());
+    put_be32(out, crc32_update(0xFFFFFFFFu, td.data(), td.size()) ^ 0xFFFFFFFFu);
+}
+extern "C" int qgmap_write_png(const char *path, const uint8_t *rgb, int M, int N)
+{
+    if (!path || !*path || !rgb || M < 1 || N < 1) return QGMAP_ERR_ARG;
+    const size_t MN = (size_t)M * N, row = 1 + 3 * (size_t)N;
+    std::vector<uint8_t> raw(row * M);                                  // scanlines: filter byte 0 + interleaved RGB
+    for (int m = 0; m < M; ++m) {
+        uint8_t *r = raw.data() + row * m;
+        r[0] = 0;
+        for (int n = 0; n < N; ++n)
+            for (int ch = 0; ch < 3; ++ch) r[1 + 3 * n + ch] = rgb[(size_t)m + (size_t)M * n + MN * ch];
+    }
+    std::vector<uint8_t> z;                                             // zlib: header, stored blocks (<= 65535 B), adler32
+    z.push_back(0x78); z.push_back(0x01);
+    uint32_t a = 1, b = 0;
+    for (size_t off = 0; off < raw.size();) {
+        const size_t n = std::min<size_t>(65535, raw.size() - off);
+        z.push_back(off + n == raw.size() ? 1 : 0);
+        z.push_back((uint8_t)(n & 0xFF)); z.push_back((uint8_t)(n >> 8));
+        z.push_back((uint8_t)(~n & 0xFF)); z.push_back((uint8_t)((~n >> 8) & 0xFF));
+        z.insert(z.end(), raw.begin() + off, raw.begin() + off + n);
+        for (size_t i = off; i < off + n; ++i) { a = (a + raw[i]) % 65521u; b = (b + a) % 65521u; }
+        off += n;
+    }
+    put_be32(z, (b << 16) | a);
+    std::vector<uint8_t> out = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+    std::vector<uint8_t> ihdr;
+    put_be32(ihdr, (uint32_t)N); put_be32(ihdr, (uint32_t)M);
+    ihdr.push_back(8); ihdr.push_back(2); ihdr.push_back(0); ihdr.push_back(0); ihdr.push_back(0);   // 8-bit, RGB
+    png_chunk(out, "IHDR", ihdr);
+    png_chunk(out, "IDAT", z);
+    png_chunk(out, "IEND", {});
+    FILE *f = std::fopen(path, "wb");
+    if (!f) return QGMAP_ERR_ARG;
+    const bool ok = std::fwrite(out.data(), 1, out.size(), f) == out.size();
+    return (std::fclose(f) == 0 && ok) ? QGMAP_OK : QGMAP_ERR_ARG;
+}
+
+// ---- Middlebury .flo (readFlowFile.m:33-81, legacy/writeFlowFile.m): tag 202021.25 ("PIEH"), int32 width, height, then
+// row-major interleaved float32 (u,v) ----
+extern "C" int qgmap_read_flo(const char *path, int *H, int *W, double *flow)
+{
+    if (!path || !H || !W) return QGMAP_ERR_ARG;
+    const size_t len = std::strlen(path);
+    if (len < 4 || std::strcmp(path + len - 4, ".flo") != 0) return QGMAP_ERR_ARG;         // readFlowFile.m:44-52
+    FILE *f = std::fopen(path, "rb");
+    if (!f) return QGMAP_ERR_ARG;
+    float tag = 0.f;
+    int32_t wh[2] = {0, 0};
+    bool ok = std::fread(&tag, 4, 1, f) == 1 && std::fread(wh, 4, 2, f) == 2 && tag == 202021.25f &&
+              wh[0] >= 1 && wh[0] <= 99999 && wh[1] >= 1 && wh[1] <= 99999;                 // readFlowFile.m:60-72
+    if (ok) {
+        *W = wh[0]; *H = wh[1];
+        if (flow) {
+            const size_t n = (size_t)wh[0] * wh[1];
+            std::vector<float> tmp(2 * n);
+            ok = std::fread(tmp.data(), 4, 2 * n, f) == 2 * n;
+            if (ok)
+                for (int r = 0; r < wh[1]; ++r)
+                    for (int c = 0; c < wh[0]; ++c) {
+                        flow[(size_t)r + (size_t)wh[1] * c] = tmp[2 * ((size_t)r * wh[0] + c)];
+                        flow[(size_t)r + (size_t)wh[1] * c + n] = tmp[2 * ((size_t)r * wh[0] + c) + 1];
+                    }
+        }
+    }
+    std::fclose(f);
+    return ok ? QGMAP_OK : QGMAP_ERR_ARG;
+}
+extern "C" int qgmap_write_flo(const char *path, const double *flow, int H, int W)
+{
+    if (!path || !flow || H < 1 || W < 1) return QGMAP_ERR_ARG;
+    const size_t len = std::strlen(path);
+    if (len < 4 || std::strcmp(path + len - 4, ".flo") != 0) return QGMAP_ERR_ARG;         // writeFlowFile.m:33-41
+    FILE *f = std::fopen(path, "wb");
+    if (!f) return QGMAP_ERR_ARG;
+    const size_t n = (size_t)H * W;
+    std::vector<float> tmp(2 * n);
+    for (int r = 0; r < H; ++r)
+        for (int c = 0; c < W; ++c) {
+            tmp[2 * ((size_t)r * W + c)] = (float)flow[(size_t)r + (size_t)H * c];
+            tmp[2 * ((size_t)r * W + c) + 1] = (float)flow[(size_t)r + (size_t)H * c + n];
+        }
+    const int32_t wh[2] = {W, H};
+    const bool ok = std::fwrite("PIEH", 1, 4, f) == 4 && std::fwrite(wh, 4, 2, f) == 2 && std::fwrite(tmp.data(), 4, 2 * n, f) == 2 * n;
+    return (std::fclose(f) == 0 && ok) ? QGMAP_OK : QGMAP_ERR_ARG;
 }
 
 extern "C" const char *qgmap_status_string(int status)

@@ -7,6 +7,7 @@
 
 struct QgMonParams;
 struct QgBand;
+struct QgP2P;
 
 struct qgmap_handle {
     qgmap_config cfg{};
@@ -46,6 +47,7 @@ struct qgmap_handle {
     bool in_group = false;         // member of a single-process qgmap_group (stepped by the group only)
     int band_steps_enqueued = 0;   // NCCL band mode: iterations enqueued since the last control-block read-back
     QgBand *band = nullptr;
+    QgP2P *p2p = nullptr;          // band mode over peer memory (qgmap_band_p2p_connect / multi-device qgmap_group)
     std::string err;
 };
 
@@ -70,6 +72,9 @@ int qgmap_band_refresh(qgmap_handle *h);                       // exchange halo 
 int qgmap_band_iteration(qgmap_handle *h, long long *launches); // one iteration incl. all-reduce + halo exchange
 void qgmap_launch_iteration(const qgmap_handle *h);             // plain iteration kernel launch on h->stream
 void qgmap_launch_advance(const qgmap_handle *h);
+void qgmap_p2p_release(qgmap_handle *h);
+void qgmap_p2p_begin_step(qgmap_handle *h);                     // new generation tag for the flags of this qgmap_step call
+int qgmap_p2p_iteration(qgmap_handle *h, long long *launches);  // iteration kernel + publish/advance kernel
 int qgmap_prepare_step(qgmap_handle *h, int n, int its);
 int qgmap_finish_step(qgmap_handle *h, double *energy, double *ptdmu, double *ptdsigma, int *n_done, int *stopped);
 void qgmap_set_last_error(const char *msg);

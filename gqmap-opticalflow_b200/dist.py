@@ -1,6 +1,7 @@
 """Multi-process plumbing (one process per GPU, torch.distributed for the rendezvous): how the two natural splits of the
 path are laid over ranks.  torch.distributed is plumbing only: the data path of a row-band run is
-NCCL send/recv + all-reduce issued by libqgmap.so itself (qgmap_band_connect); independent frame pairs need no collective.
+libqgmap's own peer-memory publish kernel (qgmap_band_p2p_connect) or NCCL send/recv + all-reduce issued by libqgmap.so
+itself (qgmap_band_connect); independent frame pairs need no collective.
 """
 import ctypes as C
 
@@ -40,11 +41,33 @@ def broadcast_unique_id(dist, device=None):
     return bytes(t.cpu().numpy().tobytes())
 
 
-def connect_band(solver, dist, device=None):
-    """Attach a Solver created with options.row_begin/row_end = band_rows(M, rank, world) to its neighbours."""
-    uid = broadcast_unique_id(dist, device)
-    buf = C.create_string_buffer(uid, 128)
-    check(lib.qgmap_band_connect(solver._h, dist.get_rank(), dist.get_world_size(), buf), solver._h)
+def connect_band(solver, dist, device=None, transport=None):
+    """Attach a Solver created with options.row_begin/row_end = band_rows(M, rank, world) to its neighbours.
+    transport 'p2p' (default; env QGMAP_BAND_TRANSPORT): libqgmap's own publish kernel stores the boundary rows and partial sums
+    into the peers' memory over NVLink (CUDA IPC mappings); 'nccl': ncclSend/ncclRecv + ncclAllReduce on libqgmap's communicator.
+    torch.distributed only carries the rendezvous data (IPC handles / NCCL id)."""
+    import os
+    transport = transport or os.environ.get("QGMAP_BAND_TRANSPORT", "p2p")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if transport == "nccl":
+        uid = broadcast_unique_id(dist, device)
+        buf = C.create_string_buffer(uid, 128)
+        check(lib.qgmap_band_connect(solver._h, rank, world, buf), solver._h)
+    elif transport == "p2p":
+        import torch
+        from ._lib import QGMAP_P2P_BLOB_BYTES as NB
+        blob = C.create_string_buffer(NB)
+        check(lib.qgmap_band_p2p_export(solver._h, blob), solver._h)
+        dev = device if device is not None else "cpu"
+        mine = torch.frombuffer(bytearray(blob.raw), dtype=torch.uint8).to(dev)
+        parts = [torch.zeros(NB, dtype=torch.uint8, device=dev) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        allb = C.create_string_buffer(b"".join(bytes(p.cpu().numpy().tobytes()) for p in parts), NB * world)
+        check(lib.qgmap_band_p2p_connect(solver._h, rank, world, allb), solver._h)
+    else:
+        raise ValueError("transport must be 'p2p' or 'nccl'")
+    dist.barrier()
+    return transport
 
 
 def assemble_bands(dist, state, M):

@@ -29,6 +29,32 @@ def readFlowFile(filename):
     return np.asfortranarray(np.stack([tmp[:, 0::2], tmp[:, 1::2]], axis=2))
 
 
+def writeFlowFile(img, filename):
+    """writeFlowFile(img, filename): H x W x 2 flow -> Middlebury .flo (legacy/writeFlowFile.m:27-76)."""
+    if not filename:
+        raise ValueError("writeFlowFile: empty filename")
+    if not filename.endswith(".flo"):
+        raise ValueError("writeFlowFile: filename %s should have extension '.flo'" % filename)
+    img = np.asarray(img)
+    if img.ndim != 3 or img.shape[2] != 2:
+        raise ValueError("writeFlowFile: image must have two bands")
+    height, width, _ = img.shape
+    with open(filename, "wb") as f:
+        f.write(b"PIEH")
+        np.array([width, height], np.int32).tofile(f)
+        tmp = np.empty((height, width * 2), np.float32)
+        tmp[:, 0::2] = img[:, :, 0]
+        tmp[:, 1::2] = img[:, :, 1]
+        tmp.tofile(f)
+
+
+def save_results(path, options, mu, sigma, alpha, AEPE, Energy, logP):
+    """save([options.dir '/' name '.mat'],'options','AEPE','mu','sigma','alpha','Energy','logP') -- optical_flow.m:28."""
+    from scipy.io import savemat
+    opts = {k: (np.asarray(v) if not isinstance(v, str) else v) for k, v in dict(options).items() if v is not None and k != "init"}
+    savemat(path, dict(options=opts, AEPE=AEPE, mu=mu, sigma=sigma, alpha=alpha, Energy=Energy, logP=logP), do_compression=True)
+
+
 def rgb2gray(rgb):
     """MATLAB rgb2gray on uint8: 0.298936021293775 R + 0.587043074451121 G + 0.114020904255103 B, rounded to uint8."""
     rgb = np.asarray(rgb)

@@ -14,7 +14,8 @@ wrappers in matlab/ and the MEX gateways in mex/ bind the very same C symbols.
 `options` is a dict (or any object with attributes) carrying the reference's fields (gqmap_gpu_mixture.m:3-6):
 trueFlow, unknownIdx, its, K, L, temperature, drate, epsn, lambdad, lambdas, minu, maxu, minv, maxv [, dir].
 New OPTIONAL fields only: init (dict of the 7 state arrays muu,muv,sigmau,sigmav,pn,rou,w), seed, alpha_mode
-('softmax'|'projsplx'), device, log_every.  Everything runs on the GPU; there is no CPU path.
+('softmax'|'projsplx'), device, log_every.  options.dir, when given, receives <it>.png at every monitored iteration
+(:59-62); the directory must exist (the drivers mkdir it, optical_flow.m:25).  Everything runs on the GPU; there is no CPU path.
 """
 import ctypes as C
 
@@ -111,9 +112,14 @@ def _solve(options, I1, I2, variant):
     Energy = np.zeros(its)
     logP = np.zeros(its)
     done = C.c_int(0)
-    check(lib.qgmap_solve(C.byref(cfg), dptr(I1), dptr(I2), Mo, No, its, init_arr,
-                          C.c_uint64(int(_opt(options, "seed", 0))), dptr(tflow), u8ptr(unk),
-                          dptr(mu), dptr(sigma), dptr(alpha), dptr(AEPE), dptr(Energy), dptr(logP), C.byref(done)))
+    out_dir = _opt(options, "dir")                  # gqmap_gpu_mixture.m:62: [options.dir '/' num2str(it) '.png']
+    check(lib.qgmap_solve_set_dump_dir(None if not out_dir else str(out_dir).encode()))
+    try:
+        check(lib.qgmap_solve(C.byref(cfg), dptr(I1), dptr(I2), Mo, No, its, init_arr,
+                              C.c_uint64(int(_opt(options, "seed", 0))), dptr(tflow), u8ptr(unk),
+                              dptr(mu), dptr(sigma), dptr(alpha), dptr(AEPE), dptr(Energy), dptr(logP), C.byref(done)))
+    finally:
+        lib.qgmap_solve_set_dump_dir(None)
     return mu, sigma, alpha.reshape(1, 1, L), AEPE.reshape(its, 1), Energy.reshape(its, 1), logP.reshape(its, 1)
 
 
@@ -164,6 +170,14 @@ def flowToColor_mex(flow, maxFlow=None):
     check(lib.qgmap_flow_to_color(dptr(flow), M, N, -1.0 if maxFlow is None else float(maxFlow),
                                   u8ptr(img), dptr(flo), dptr(stats), u8ptr(unk)))
     return img, flo, stats[0], stats[1], stats[2], stats[3], unk.astype(bool)
+
+
+def imwrite(img, filename):
+    """imwrite(flc, filename) for the M x N x 3 uint8 images flowToColor_mex returns (gqmap_gpu_mixture.m:62)."""
+    img = np.asfortranarray(np.asarray(img, dtype=np.uint8))
+    if img.ndim != 3 or img.shape[2] != 3:
+        raise ValueError("imwrite: M x N x 3 uint8 image expected")
+    check(lib.qgmap_write_png(str(filename).encode(), u8ptr(img), img.shape[0], img.shape[1]))
 
 
 def GaussHermite_2(n):

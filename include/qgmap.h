@@ -150,6 +150,19 @@ int qgmap_find_map(const double *alpha, const double *mu_u, const double *sig_u,
 int qgmap_flow_to_color(const double *flow, int M, int N, double max_flow,
                         uint8_t *img, double *flo, double *stats, uint8_t *unknown);
 
+/* imwrite(flc, [options.dir '/' num2str(it) '.png']) replacement (gqmap_gpu_mixture.m:62, gqmap_gpuSuper_mix_entropy.m:61):
+ * 8-bit RGB PNG of a column-major M x N x 3 uint8 image (what qgmap_flow_to_color returns).  Host C++, no zlib needed
+ * (stored deflate blocks). */
+int qgmap_write_png(const char *path, const uint8_t *rgb, int M, int N);
+/* options.dir of the one-call solver (gqmap_gpu_mixture.m:62): while set (per host thread; NULL or "" clears it), qgmap_solve
+ * writes <dir>/<it>.png -- the colour-coded MAP flow, for the super-pixel variant repelem(map,4,4) cropped 5:end-4 (S:58-61) --
+ * at it == 1 and every log_every iterations.  The directory must exist (the reference's drivers mkdir it, optical_flow.m:25). */
+int qgmap_solve_set_dump_dir(const char *dir);
+/* readFlowFile.m:33-81 / legacy/writeFlowFile.m: Middlebury .flo <-> column-major H x W x 2 doubles.
+ * qgmap_read_flo: call with flow == NULL to get the size, then with a buffer of H*W*2 doubles. */
+int qgmap_read_flo(const char *path, int *H, int *W, double *flow);
+int qgmap_write_flo(const char *path, const double *flow, int H, int W);
+
 /* Gauss-Hermite nodes/weights, GaussHermite_2.m:21-32 ([x,w] = GaussHermite_2(n)), n <= QGMAP_KMAX. */
 int qgmap_gauss_hermite(int n, double *x, double *w);
 /* projsplx.m:15-32: Euclidean projection of y (length m) onto the probability simplex. */
@@ -167,6 +180,18 @@ int qgmap_debug_gradients(qgmap_handle *h, double *G_muu, double *G_muv, double 
  * qgmap_band_unique_id() on rank 0 and distributed by the host (torch.distributed / MATLAB parpool / files). */
 int qgmap_band_unique_id(void *id128);
 int qgmap_band_connect(qgmap_handle *h, int rank, int nranks, const void *nccl_unique_id);
+/* The same decomposition WITHOUT NCCL on the data path: every rank maps its two neighbours' state buffers and every rank's
+ * small mailbox (CUDA IPC across processes, plain peer access inside one process).  Per iteration ONE extra kernel stores the
+ * band's boundary rows straight into the neighbours' halo rows over NVLink, posts the band's 4L partial sums into every
+ * rank's mailbox, raises a flag, waits for the other ranks' flags, sums in fixed rank order (bit-identical on all ranks) and
+ * advances the control block.  No host involvement, two launches per iteration.  Protocol: every rank calls
+ * qgmap_band_p2p_export (fills QGMAP_P2P_BLOB_BYTES), the host all-gathers the blobs (torch.distributed / files), every rank
+ * calls qgmap_band_p2p_connect with the nranks blobs in rank order, then a host barrier before the first step.  All ranks must
+ * issue the same qgmap_step calls.  A rank that does not hear from a peer within ~10 s stops with QGMAP_ERR_COMM. */
+#define QGMAP_P2P_BLOB_BYTES 512
+#define QGMAP_P2P_RANKS_MAX 16
+int qgmap_band_p2p_export(qgmap_handle *h, void *blob);
+int qgmap_band_p2p_connect(qgmap_handle *h, int rank, int nranks, const void *blobs);
 
 /* The same decomposition driven by ONE process (the natural model for a MATLAB host; also how it is tested on one GPU):
  * nbands handles, band b on devices[b] (NULL: all on the current device), halo rows copied peer-to-peer between the bands'

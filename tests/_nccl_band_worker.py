@@ -1,4 +1,5 @@
-"""Worker for tests/test_gpu_multirank.py: one process per GPU, row bands of ONE frame pair over NCCL (qgmap_band_connect).
+"""Worker for tests/test_gpu_multirank.py: one process per GPU, row bands of ONE frame pair, both transports: libqgmap's own
+peer-memory publish kernel (qgmap_band_p2p_connect, CUDA IPC) and NCCL (qgmap_band_connect).
 Rank 0 also solves the undivided problem and checks the assembled band result is bit-identical."""
 import importlib
 import os
@@ -21,16 +22,19 @@ def main():
     pkg = importlib.import_module("gqmap-opticalflow_b200")
     from oracle import oracle as O
     from conftest import make_problem, options_from_cfg, state_dict
-    for variant, (Mo, No), L, K, T in (("full", (75, 90), 2, 5, 0.0), ("super", (128, 160), 3, 3, 0.2)):
+    for transport, variant, (Mo, No), L, K, T in (("p2p", "full", (75, 90), 2, 5, 0.0), ("p2p", "super", (128, 160), 3, 3, 0.2),
+                                                  ("nccl", "full", (75, 90), 2, 5, 0.0), ("nccl", "super", (128, 160), 3, 3, 0.2)):
         sup = variant == "super"
         cfg, I1, I2, st = make_problem(O, Mo, No, L, K, super=sup, seed=23, T=T, small_sigma=True)
         rb, re = pkg.dist.band_rows(cfg.M, rank, world)
         opts = options_from_cfg(cfg, T=T, alpha_scale=1e-5, device=local)
         n = 12
         with pkg.Solver(dict(opts, row_begin=rb, row_end=re), I1, I2, variant=variant) as s:
-            pkg.dist.connect_band(s, dist)
+            pkg.dist.connect_band(s, dist, transport=transport)
             s.set_state(state_dict(st), T=T, it=495)
-            r = s.step(n)
+            r = s.step(5)                                   # two step calls: the p2p flags carry a per-call generation
+            r2 = s.step(n - 5)
+            r = dict(n_done=r["n_done"] + r2["n_done"], Energy=np.concatenate([r["Energy"], r2["Energy"]]), ms=r["ms"] + r2["ms"])
             full = pkg.dist.assemble_bands(dist, s.get_state(), cfg.M)
         assert r["n_done"] == n, r
         if rank == 0:
@@ -42,7 +46,7 @@ def main():
                 assert np.array_equal(a[f], full[f]), (variant, f, np.abs(a[f] - full[f]).max())
             assert np.abs(r["Energy"] / r1["Energy"] - 1).max() < 1e-12
             assert np.abs(full["alpha"] - a["alpha"]).max() < 1e-14
-            print("nccl bands %s world=%d: bit-identical to the single domain, %.3f ms/it" % (variant, world, r["ms"] / n), flush=True)
+            print("%s bands %s world=%d: bit-identical to the single domain, %.3f ms/it" % (transport, variant, world, r["ms"] / n), flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

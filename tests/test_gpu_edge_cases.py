@@ -82,3 +82,33 @@ def test_zero_weight_component(pkg, O):
         assert np.all(d[name][:, :, 1] == 0)
     assert np.all(g["dmuu"][1:-1, 1:-1, 1] == 0)
     assert np.abs(d["G_muu"][1:-1, 1:-1, 0] - g["dmuu"][1:-1, 1:-1, 0]).max() < 4e-4 * np.abs(g["dmuu"]).max()
+
+
+@pytest.mark.parametrize("variant", ["full", "super"])
+def test_options_dir_receives_flow_pngs(pkg, O, variant, tmp_path):
+    """options.dir (gqmap_gpu_mixture.m:59-62, S:58-61): <it>.png at it==1 and every log_every iterations holds
+    flowToColor_mex of the MAP flow (super: repelem(map,4,4) cropped 5:end-4)."""
+    from PIL import Image
+    sup = variant == "super"
+    M, N = (48, 64) if sup else (24, 30)
+    I1, I2, flow, (minu, maxu, minv, maxv) = pkg.synthetic_pair(M, N)
+    opts = dict(K=3, L=2, its=9, temperature=0.2 if sup else 0.0, drate=0.75, epsn=1e-6, lambdad=1.0, lambdas=5.0,
+                minu=minu, maxu=maxu, minv=minv, maxv=maxv, seed=3, log_every=4, dir=str(tmp_path))
+    fn = pkg.gqmap_gpuSuper_mix_entropy if sup else pkg.gqmap_gpu_mixture
+    mu, sigma, alpha, AEPE, Energy, logP = fn(opts, I1, I2)
+    assert sorted(p.name for p in tmp_path.iterdir()) == ["1.png", "4.png", "8.png"]
+    want = (M - 8, N - 8, 3) if sup else (M, N, 3)
+    for p in tmp_path.iterdir():
+        assert np.asarray(Image.open(str(p))).shape == want
+    # the it==8 image from the returned beliefs is not reproducible (beliefs moved on to it 9); re-run to exactly 8 iterations
+    d2 = tmp_path / "second"
+    d2.mkdir()
+    mu, sigma, alpha, *_ = fn(dict(opts, its=8, dir=str(d2)), I1, I2)
+    mp = pkg.get_map_mex(alpha.ravel(), mu[..., 0], sigma[..., 0], mu[..., 1], sigma[..., 1])
+    if sup:
+        mp = np.repeat(np.repeat(mp, 4, axis=0), 4, axis=1)[4:-4, 4:-4]
+    img = pkg.flowToColor_mex(np.asfortranarray(mp))[0]
+    got = np.asarray(Image.open(str(d2 / "8.png")))
+    assert (got != img).mean() < 0.01        # fp32-state vs returned-fp64 rounding may flip a colour level on a few pixels
+    with pytest.raises(pkg.QgmapError):
+        fn(dict(opts, dir=str(tmp_path / "missing")), I1, I2)

@@ -1,4 +1,5 @@
-"""Multi-process row bands over NCCL (one process per GPU).  Needs >= 2 GPUs: run with `gpurun --gpus 2`."""
+"""Row bands over several GPUs: multi-process (one process per GPU; peer-memory publish kernel and NCCL transports) and the
+single-process band group with one band per GPU.  Needs >= 2 GPUs: run with `gpurun --gpus 2`."""
 import os
 import subprocess
 import sys
@@ -17,4 +18,36 @@ def test_nccl_bands_two_ranks():
            "--master-port", "29621", os.path.join("tests", "_nccl_band_worker.py")]
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("bit-identical") == 2
+    assert r.stdout.count("bit-identical") == 4
+
+
+@pytest.mark.gpu
+def test_group_one_band_per_gpu_is_bit_identical():
+    """qgmap_group with every band on its own GPU uses the peer-memory publish kernel (qgmap_p2p.cu): same bits as one domain."""
+    import importlib
+    import numpy as np
+    import torch
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, ROOT)
+    pkg = importlib.import_module("gqmap-opticalflow_b200")
+    from oracle import oracle as O
+    from conftest import make_problem, options_from_cfg, state_dict
+    nb = min(ndev, 4)
+    for variant, (Mo, No), L, K, T in (("full", (67, 90), 2, 5, 0.0), ("super", (128, 160), 3, 3, 0.2)):
+        cfg, I1, I2, st = make_problem(O, Mo, No, L, K, super=variant == "super", seed=29, T=T, small_sigma=True)
+        opts = options_from_cfg(cfg, T=T, alpha_scale=1e-5)
+        with pkg.Solver(opts, I1, I2, variant=variant) as s1:
+            s1.set_state(state_dict(st), T=T, it=495)
+            r1 = s1.step(14)
+            a = s1.get_state()
+        with pkg.BandGroup(opts, I1, I2, nb, devices=list(range(nb)), variant=variant) as g:
+            g.set_state(state_dict(st), T=T, it=495)
+            ra = g.step(6)
+            rb = g.step(8)
+            b = g.get_state()
+        for f in ("muu", "muv", "sigmau", "sigmav", "pn", "rou"):
+            assert np.array_equal(a[f], b[f]), (variant, f)
+        E = np.concatenate([ra["Energy"], rb["Energy"]])
+        assert np.abs(E / r1["Energy"] - 1).max() < 1e-12 and np.abs(a["alpha"] - b["alpha"]).max() < 1e-14

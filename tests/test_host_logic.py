@@ -94,3 +94,56 @@ def test_mex_gateways_compile_against_stub():
     subprocess.check_call(["make", "-C", mexdir, "-B"], stdout=subprocess.DEVNULL)
     for f in ("gqmap_mex.o", "get_map_mex.o", "flowToColor_mex.o"):
         assert os.path.exists(os.path.join(mexdir, f))
+
+
+def test_png_writer_round_trips(pkg, tmp_path):
+    """imwrite replacement (gqmap_gpu_mixture.m:62): the PNG decodes (PIL) to exactly the image flowToColor_mex produced."""
+    from PIL import Image
+    rng = np.random.default_rng(3)
+    for shape in ((1, 1), (7, 300), (388, 584)):                       # last one needs several stored deflate blocks
+        img = rng.integers(0, 256, shape + (3,), dtype=np.uint8)
+        p = str(tmp_path / ("t%dx%d.png" % shape))
+        pkg.imwrite(img, p)
+        back = np.asarray(Image.open(p))
+        assert back.shape == shape + (3,) and np.array_equal(back, img)
+    with pytest.raises(pkg.QgmapError):
+        pkg.imwrite(img, str(tmp_path / "no_such_dir" / "x.png"))
+    with pytest.raises(ValueError):
+        pkg.imwrite(img[:, :, 0], str(tmp_path / "y.png"))
+
+
+def test_flo_files_round_trip(pkg, tmp_path):
+    """readFlowFile.m / legacy/writeFlowFile.m: Python mirror and C ABI write identical files and read each other's."""
+    import ctypes as C
+    rng = np.random.default_rng(4)
+    flow = np.asfortranarray(rng.normal(0, 5, (13, 29, 2)).astype(np.float32).astype(np.float64))
+    flow[3, 4] = 1.6e9                                                  # unknown-flow marker survives (float32)
+    a, b = str(tmp_path / "a.flo"), str(tmp_path / "b.flo")
+    pkg.writeFlowFile(flow, a)
+    lib = pkg._lib.lib
+    assert lib.qgmap_write_flo(b.encode(), pkg._lib.dptr(flow), 13, 29) == 0
+    assert open(a, "rb").read() == open(b, "rb").read()
+    assert open(a, "rb").read(4) == b"PIEH" and struct.unpack("<f", b"PIEH")[0] == 202021.25
+    assert np.array_equal(pkg.readFlowFile(b), flow)
+    H, W = C.c_int(), C.c_int()
+    assert lib.qgmap_read_flo(a.encode(), C.byref(H), C.byref(W), None) == 0 and (H.value, W.value) == (13, 29)
+    out = np.zeros((13, 29, 2), order="F")
+    assert lib.qgmap_read_flo(a.encode(), C.byref(H), C.byref(W), pkg._lib.dptr(out)) == 0 and np.array_equal(out, flow)
+    assert lib.qgmap_read_flo(str(tmp_path / "a.txt").encode(), C.byref(H), C.byref(W), None) != 0       # extension check
+    open(str(tmp_path / "bad.flo"), "wb").write(b"XXXX" + bytes(8))
+    assert lib.qgmap_read_flo(str(tmp_path / "bad.flo").encode(), C.byref(H), C.byref(W), None) != 0     # wrong tag
+    with pytest.raises(ValueError):
+        pkg.writeFlowFile(flow[:, :, :1], a)
+    with pytest.raises(ValueError):
+        pkg.writeFlowFile(flow, str(tmp_path / "a.dat"))
+
+
+def test_save_results_schema(pkg, tmp_path):
+    """optical_flow.m:28: the .mat carries options, AEPE, mu, sigma, alpha, Energy, logP."""
+    from scipy.io import loadmat
+    p = str(tmp_path / "r.mat")
+    opts = dict(K=3, L=2, its=5, dir="x", lambdas=5.0)
+    pkg.save_results(p, opts, np.zeros((4, 5, 2, 2)), np.ones((4, 5, 2, 2)), np.full((1, 1, 2), 0.5), np.zeros((5, 1)), np.zeros((5, 1)), np.zeros((5, 1)))
+    m = loadmat(p)
+    assert {"options", "AEPE", "mu", "sigma", "alpha", "Energy", "logP"} <= set(m)
+    assert m["mu"].shape == (4, 5, 2, 2) and m["alpha"].shape == (1, 1, 2) and int(m["options"]["K"][0, 0][0, 0]) == 3
