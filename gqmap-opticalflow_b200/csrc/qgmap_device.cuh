@@ -68,6 +68,12 @@ __device__ __forceinline__ float2 qg_neg2(float2 v) { return make_float2(-v.x, -
 // (p[c] = (VV(y, x+c), VV(y+1, x+c))), so that one FFMA2 with a broadcast column weight advances both rows.
 struct __align__(32) QgTap8 { float2 p[4]; };
 
+// State loads: each value is read once per iteration, so it must not displace the gather entries in L1 (+1.3% at K=5).
+__device__ __forceinline__ float qg_lds(const float *ptr) {
+    float v;
+    asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(ptr));
+    return v;
+}
 // sm_100 256-bit read-only global load (SASS LDG.E.ENL2.256.CONSTANT)
 __device__ __forceinline__ QgTap8 qg_ld256(const QgTap8 *ptr) {
     QgTap8 v;
