@@ -10,3 +10,5 @@ from .host import (gqmap_gpu_mixture, gqmap_gpuSuper_mix_entropy, get_map_mex, f
                    GaussHermite_2, projsplx, imwrite, Solver, make_config, last_solve_stats, batch_step, fp32_peak, BandGroup)
 from .frames import readFlowFile, writeFlowFile, save_results, rgb2gray, synthetic_pair, middlebury_shapes                     # noqa: F401
 from . import dist                                    # noqa: F401,E402
+from . import ctf                                     # noqa: F401,E402
+from .ctf import optical_flow_ctf, gqmap_ctf          # noqa: F401,E402

@@ -34,7 +34,7 @@ class QgmapConfig(C.Structure):
         ("minu", C.c_double), ("maxu", C.c_double), ("minv", C.c_double), ("maxv", C.c_double),
         ("sigma_min", C.c_double), ("sigma_max", C.c_double), ("corr_tor", C.c_double),
         ("step0", C.c_double), ("step_tau", C.c_double), ("alpha_scale", C.c_double),
-        ("T_floor", C.c_double), ("tor", C.c_double),
+        ("T_floor", C.c_double), ("tor", C.c_double), ("sigma_step_scale", C.c_double),
         ("alpha_start", C.c_int32), ("alpha_mode", C.c_int32), ("anneal_every", C.c_int32),
         ("device", C.c_int32), ("row_begin", C.c_int32), ("row_end", C.c_int32), ("log_every", C.c_int32),
     ]

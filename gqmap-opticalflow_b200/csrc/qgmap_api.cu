@@ -59,7 +59,7 @@ extern "C" int qgmap_config_defaults(qgmap_config *c, int variant)
     c->sigma_min = 0.01; c->sigma_max = sup ? 25.0 : 23.0;
     c->corr_tor = 1.0 - 1e-5;
     c->step0 = sup ? 0.001 : 0.1; c->step_tau = sup ? 4000.0 : 8000.0;
-    c->alpha_scale = 1e-7; c->T_floor = 0.001; c->tor = 1e-4;
+    c->alpha_scale = 1e-7; c->T_floor = 0.001; c->tor = 1e-4; c->sigma_step_scale = 1.0;
     c->alpha_start = 500; c->alpha_mode = QGMAP_ALPHA_SOFTMAX;
     c->anneal_every = sup ? 500 : 0;
     c->device = -1; c->row_begin = 0; c->row_end = 0; c->log_every = 300;
@@ -265,7 +265,7 @@ extern "C" int qgmap_create(const qgmap_config *cfg, const double *I1, const dou
     p.minu = (float)cfg->minu; p.maxu = (float)cfg->maxu; p.minv = (float)cfg->minv; p.maxv = (float)cfg->maxv;
     p.sig_min = (float)cfg->sigma_min; p.sig_max = (float)cfg->sigma_max; p.corr_tor = (float)cfg->corr_tor;
     p.step0 = cfg->step0; p.step_tau = cfg->step_tau; p.alpha_scale = cfg->alpha_scale; p.drate = cfg->drate;
-    p.T_floor = cfg->T_floor; p.tor = cfg->tor; p.alpha_start = cfg->alpha_start; p.alpha_mode = cfg->alpha_mode;
+    p.sig_step = (float)cfg->sigma_step_scale; p.T_floor = cfg->T_floor; p.tor = cfg->tor; p.alpha_start = cfg->alpha_start; p.alpha_mode = cfg->alpha_mode;
     p.anneal_every = cfg->anneal_every;
     p.ctrl = h->ctrl; p.partials = h->partials;
     QG_CUDA_C(cudaStreamSynchronize(h->stream));

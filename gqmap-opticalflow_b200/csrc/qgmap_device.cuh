@@ -120,7 +120,7 @@ struct QgIterParams {
     int K;                             // quadrature order (runtime copy)
     int band;                          // 1: defer control update to the finalize kernel (after all-reduce)
     float lambdad, lambdas, epsn;
-    float minu, maxu, minv, maxv, sig_min, sig_max, corr_tor;
+    float minu, maxu, minv, maxv, sig_min, sig_max, corr_tor, sig_step;
     double step0, step_tau;
     double alpha_scale, drate, T_floor, tor;
     int alpha_start, alpha_mode, anneal_every;

@@ -227,8 +227,8 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
         } else {                                                                 // :41-44, :46
             o[F_MUU * fstr] = qg_clamp(fmaf(G_muu, step, muu), p.minu, p.maxu);
             o[F_MUV * fstr] = qg_clamp(fmaf(G_muv, step, muv), p.minv, p.maxv);
-            o[F_SIGU * fstr] = qg_clamp(fmaf(G_sigu, step, sigu), p.sig_min, p.sig_max);
-            o[F_SIGV * fstr] = qg_clamp(fmaf(G_sigv, step, sigv), p.sig_min, p.sig_max);
+            o[F_SIGU * fstr] = qg_clamp(fmaf(G_sigu, step * p.sig_step, sigu), p.sig_min, p.sig_max);
+            o[F_SIGV * fstr] = qg_clamp(fmaf(G_sigv, step * p.sig_step, sigv), p.sig_min, p.sig_max);
             o[F_PN * fstr] = qg_clamp(fmaf(gn.dp, step, pn), -p.corr_tor, p.corr_tor);
         }
     }
@@ -362,14 +362,14 @@ qgmap_iter_kernel_g4(const __grid_constant__ QgIterParams p)
             if (DUMP) { d[0 * fstr] = G_mu; d[2 * fstr] = G_sig; d[4 * fstr] = gn.dp; d[9 * fstr] = e_px; d[10 * fstr] = da_px; }
             else {
                 o[F_MUU * fstr] = qg_clamp(fmaf(G_mu, step, muu), p.minu, p.maxu);
-                o[F_SIGU * fstr] = qg_clamp(fmaf(G_sig, step, sigu), p.sig_min, p.sig_max);
+                o[F_SIGU * fstr] = qg_clamp(fmaf(G_sig, step * p.sig_step, sigu), p.sig_min, p.sig_max);
                 o[F_PN * fstr] = qg_clamp(fmaf(gn.dp, step, pn), -p.corr_tor, p.corr_tor);
             }
         } else if (g == 2) {
             if (DUMP) { d[1 * fstr] = G_mu; d[3 * fstr] = G_sig; }
             else {
                 o[F_MUV * fstr] = qg_clamp(fmaf(G_mu, step, muv), p.minv, p.maxv);
-                o[F_SIGV * fstr] = qg_clamp(fmaf(G_sig, step, sigv), p.sig_min, p.sig_max);
+                o[F_SIGV * fstr] = qg_clamp(fmaf(G_sig, step * p.sig_step, sigv), p.sig_min, p.sig_max);
             }
         }
     }

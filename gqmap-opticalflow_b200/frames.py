@@ -100,7 +100,7 @@ def _bicubic(V, yq, xq):
     return out
 
 
-def synthetic_pair(M, N, seed=1234):
+def synthetic_pair(M, N, seed=1234, flow_scale=1.0):
     """Synthetic frame pair of SURVEY.md section 8d: I1 = Gaussian-blurred (sigma 1.5) uniform noise scaled to [0,255];
     ground-truth flow u = 3 sin(2 pi row/M) + 1 (horizontal), v = 2 cos(2 pi col/N) (vertical); I2 = I1 warped so that
     I2(row+v, col+u) = I1(row,col) (bicubic resampling of I1 at the inverse flow, found by fixed-point iteration).
@@ -110,8 +110,8 @@ def synthetic_pair(M, N, seed=1234):
     I1 = (a - a.min()) / (a.max() - a.min()) * 255.0
     rows = np.arange(M, dtype=np.float64).reshape(M, 1)
     cols = np.arange(N, dtype=np.float64).reshape(1, N)
-    fu = lambda r, c: 3.0 * np.sin(2 * np.pi * r / M) + 1.0 + 0.0 * c
-    fv = lambda r, c: 2.0 * np.cos(2 * np.pi * c / N) + 0.0 * r
+    fu = lambda r, c: flow_scale * (3.0 * np.sin(2 * np.pi * r / M) + 1.0) + 0.0 * c      # flow_scale > 1: large displacements
+    fv = lambda r, c: flow_scale * (2.0 * np.cos(2 * np.pi * c / N)) + 0.0 * r            # (coarse-to-fine workloads)
     u, v = fu(rows, cols), fv(rows, cols)
     # I2(q) = I1(p) with p + flow(p) = q: invert the (smooth, contractive) flow by fixed-point iteration
     pr, pc = rows - v, cols - u

@@ -57,7 +57,7 @@ def make_config(options, variant):
     cfg.alpha_mode = _lib.ALPHA_PROJSPLX if mode == "projsplx" else _lib.ALPHA_SOFTMAX
     cfg.device = int(_opt(options, "device", -1))
     cfg.log_every = int(_opt(options, "log_every", 300))
-    for k in ("sigma_min", "sigma_max", "corr_tor", "step0", "step_tau", "alpha_scale", "T_floor", "tor"):
+    for k in ("sigma_min", "sigma_max", "corr_tor", "step0", "step_tau", "alpha_scale", "T_floor", "tor", "sigma_step_scale"):
         v = _opt(options, k)
         if v is not None:
             setattr(cfg, k, float(v))

@@ -50,6 +50,14 @@ static inline void qg_config_from_options(const mxArray *opt, int variant, qgmap
     cfg->minv = qg_field(opt, "minv", 1, 0); cfg->maxv = qg_field(opt, "maxv", 1, 0);
     cfg->device = (int)qg_field(opt, "device", 0, -1);
     cfg->log_every = (int)qg_field(opt, "log_every", 0, 300);
+    /* the constants the reference hard-codes, overridable through optional fields of the same names as qgmap_config */
+    cfg->sigma_min = qg_field(opt, "sigma_min", 0, cfg->sigma_min); cfg->sigma_max = qg_field(opt, "sigma_max", 0, cfg->sigma_max);
+    cfg->corr_tor = qg_field(opt, "corr_tor", 0, cfg->corr_tor);
+    cfg->step0 = qg_field(opt, "step0", 0, cfg->step0); cfg->step_tau = qg_field(opt, "step_tau", 0, cfg->step_tau);
+    cfg->alpha_scale = qg_field(opt, "alpha_scale", 0, cfg->alpha_scale); cfg->T_floor = qg_field(opt, "T_floor", 0, cfg->T_floor);
+    cfg->tor = qg_field(opt, "tor", 0, cfg->tor); cfg->sigma_step_scale = qg_field(opt, "sigma_step_scale", 0, cfg->sigma_step_scale);
+    cfg->alpha_start = (int)qg_field(opt, "alpha_start", 0, cfg->alpha_start);
+    cfg->anneal_every = (int)qg_field(opt, "anneal_every", 0, cfg->anneal_every);
     const mxArray *am = mxGetField(opt, 0, "alpha_mode");
     if (am && mxIsChar(am)) {
         char *sname = mxArrayToString(am);

@@ -61,6 +61,7 @@ typedef struct {
     double alpha_scale;             /* 1e-7 (:83)                                                          */
     double T_floor;                 /* 0.001 (S:72)                                                        */
     double tor;                     /* 1e-4 (:25) stop when mean|dmu_u| < tor                              */
+    double sigma_step_scale;        /* 1 (:43-44); legacy/gqmap_ctf.m:48-49 steps sigma with step*0.3      */
     int32_t alpha_start;            /* alpha updates when it > 500 (:50)                                   */
     int32_t alpha_mode;             /* QGMAP_ALPHA_*                                                       */
     int32_t anneal_every;           /* 0 = never (full-res, :73 commented) ; 500 (S:72)                    */

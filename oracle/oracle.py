@@ -37,7 +37,7 @@ class QoConfig(C.Structure):
         ("step0", C.c_double), ("step_tau", C.c_double),
         ("alpha_start", C.c_int), ("alpha_scale", C.c_double), ("alpha_mode", C.c_int),
         ("anneal_every", C.c_int), ("drate", C.c_double), ("T_floor", C.c_double), ("tor", C.c_double),
-        ("guard_a0", C.c_int), ("nthreads", C.c_int),
+        ("sigma_step_scale", C.c_double), ("guard_a0", C.c_int), ("nthreads", C.c_int),
     ]
 
 
@@ -93,6 +93,7 @@ def make_config(Mo, No, L, K, *, super=False, lambdad=1.0, lambdas=5.0, epsn=1e-
     c.alpha_start, c.alpha_scale, c.alpha_mode = 500, 1e-7, alpha_mode
     c.anneal_every = 500 if super else 0
     c.drate, c.T_floor, c.tor = drate, 0.001, 1e-4
+    c.sigma_step_scale = 1.0
     c.guard_a0 = 0 if super else 1
     c.nthreads = nthreads
     for k, v in over.items():

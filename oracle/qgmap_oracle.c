@@ -397,8 +397,8 @@ int qo_run(const qo_config *c, const double *I1, const double *VV, qo_state *s,
                     long idx = m + M * n + MN * l;
                     s->muu[idx]  = clampd(s->muu[idx]  + g.dmuu[idx] * step, c->minu, c->maxu);          /* :41 */
                     s->muv[idx]  = clampd(s->muv[idx]  + g.dmuv[idx] * step, c->minv, c->maxv);          /* :42 */
-                    s->sigu[idx] = clampd(s->sigu[idx] + g.dsigmau[idx] * step, c->sigma_min, c->sigma_max);   /* :43 */
-                    s->sigv[idx] = clampd(s->sigv[idx] + g.dsigmav[idx] * step, c->sigma_min, c->sigma_max);   /* :44 */
+                    s->sigu[idx] = clampd(s->sigu[idx] + g.dsigmau[idx] * step * c->sigma_step_scale, c->sigma_min, c->sigma_max);   /* :43 */
+                    s->sigv[idx] = clampd(s->sigv[idx] + g.dsigmav[idx] * step * c->sigma_step_scale, c->sigma_min, c->sigma_max);   /* :44 */
                     for (int q = 0; q < 4; ++q) {                                                         /* :45 */
                         long eidx = idx + MNL * q;
                         s->rou[eidx] = clampd(s->rou[eidx] + g.drou[eidx] * step, -c->corr_tor, c->corr_tor);

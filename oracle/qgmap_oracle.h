@@ -36,6 +36,7 @@ typedef struct {
     int    anneal_every;           /* 0 = off (full :73 is commented), 500 (super :72)            */
     double drate, T_floor;         /* T = max(T*drate, T_floor); floor 0.001 (super :72)          */
     double tor;                    /* 1e-4 stop tolerance (:25)                                   */
+    double sigma_step_scale;       /* 1 (:43-44); legacy/gqmap_ctf.m:48-49 uses step*0.3          */
     int    guard_a0;               /* full-res node/edge loops skip accumulators when a==0 (:98)  */
     int    nthreads;               /* OpenMP threads (0 = default)                                */
 } qo_config;

@@ -112,3 +112,46 @@ def test_options_dir_receives_flow_pngs(pkg, O, variant, tmp_path):
     assert (got != img).mean() < 0.01        # fp32-state vs returned-fp64 rounding may flip a colour level on a few pixels
     with pytest.raises(pkg.QgmapError):
         fn(dict(opts, dir=str(tmp_path / "missing")), I1, I2)
+
+
+def test_ctf_solver_constants_match_oracle(pkg, O):
+    """legacy/gqmap_ctf.m:36,46-51: constant step 0.07, sigma stepped with step*0.3, sigma <= 25, correlation clamp 0.999, L=1,
+    K=11 -- the same iteration kernel with other constants; per-step parity against the oracle with the same constants."""
+    from test_gpu_parity import _assert_state_close, _round_state
+    cfg, I1, I2, st = make_problem(O, 40, 52, 1, 11, seed=61, small_sigma=True)
+    over = dict(step0=0.07, step_tau=1e300, sigma_step_scale=0.3, sigma_max=25.0, corr_tor=0.999)
+    for k, v in over.items():
+        setattr(cfg, k, v)
+    VV = O.get_vv(I2)
+    ref = st.copy()
+    with pkg.Solver(options_from_cfg(cfg, **over), I1, I2) as s:
+        for it in (1, 2, 3, 4000):
+            before = _round_state(ref).copy()
+            s.set_state(state_dict(before), it=it, alpha=before.alpha)
+            _, _, _, E, dm, ds = O.run(cfg, I1, VV, ref, it, 10 ** 6, 1)
+            r = s.step(1)
+            got = s.get_state()
+            assert abs(r["Energy"][0] / E[0] - 1) < 1e-5 and abs(r["ptdmu"][0] / dm[0] - 1) < 1e-4
+            _assert_state_close(O, cfg, I1, VV, got, ref, before, 0.07, where=it)
+            # sigma really moved with 0.3 x the step of the means
+            d_ref = ref.sigu - before.sigu
+            assert np.abs(got["sigmau"] - before.sigu - d_ref)[1:-1, 1:-1].max() < 2e-5 + 1e-3 * np.abs(d_ref).max()
+
+
+def test_coarse_to_fine_driver_runs_on_the_cuda_solver(pkg):
+    """legacy/optical_flow_ctf.m:21-36 around the CUDA solver: level shapes, iteration budget per level, accumulated warp;
+    deterministic for a fixed seed.  (What the pyramid glue computes is pinned on the CPU by test_ctf_pyramid_glue_is_consistent;
+    how well gqmap_ctf's constants converge is a property of the legacy schedule, reported in profiles/, not asserted.)"""
+    M, N = 96, 128
+    I1, I2, flow, rng_ = pkg.synthetic_pair(M, N, seed=5, flow_scale=2.0)
+    opts = dict(K=5, its=200, epsn=1e-6, lambdas=5.0, lambdad=1.0)
+    warp, levels = pkg.optical_flow_ctf(I1, I2, flow, opts, scales=(1 / 4, 1 / 2, 1), seed=1)
+    assert warp.shape == (M, N, 2) and np.isfinite(warp).all()
+    assert [lv["shape"] for lv in levels] == [(24, 32), (48, 64), (96, 128)] and all(lv["iterations"] == 200 for lv in levels)
+    assert all(np.isfinite(lv["aepe_after"]) for lv in levels)
+    warp2, _ = pkg.optical_flow_ctf(I1, I2, flow, opts, scales=(1 / 4, 1 / 2, 1), seed=1)
+    assert np.array_equal(warp, warp2)
+    mu, sigma, rou, AEPE, Energy = pkg.gqmap_ctf(opts, I1, I2, flow, seed=1)
+    assert mu.shape == (M, N, 2) and sigma.shape == (M, N, 2) and rou.shape == (M, N, 2, 2) and np.count_nonzero(Energy) == 200
+    assert sigma.max() <= 25.0 and np.abs(rou).max() <= 0.999 + 1e-6                          # gqmap_ctf.m:48-51 clamps
+    assert mu[..., 0].min() >= flow[..., 0].min() - 1e-5 and mu[..., 0].max() <= flow[..., 0].max() + 1e-5   # :4,:46 clamp range

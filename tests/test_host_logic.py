@@ -147,3 +147,60 @@ def test_save_results_schema(pkg, tmp_path):
     m = loadmat(p)
     assert {"options", "AEPE", "mu", "sigma", "alpha", "Energy", "logP"} <= set(m)
     assert m["mu"].shape == (4, 5, 2, 2) and m["alpha"].shape == (1, 1, 2) and int(m["options"]["K"][0, 0][0, 0]) == 3
+
+
+def test_ctf_host_glue(pkg):
+    """legacy/optical_flow_ctf.m:22-30 host glue: imresize (bicubic, antialiased), interp2 (linear, NaN outside), fillmissing."""
+    from PIL import Image
+    c = pkg.ctf
+    rng = np.random.default_rng(0)
+    A = rng.random((48, 64)) * 255
+    assert np.allclose(c.imresize(A, 1.0), A, atol=1e-12)
+    for sc in (0.5, 0.25, 2.0):
+        assert np.allclose(c.imresize(np.full((20, 30), 7.0), sc), 7.0, atol=1e-12)                # weights are normalised
+        B = c.imresize(A, sc)
+        assert B.shape == (int(np.ceil(48 * sc)), int(np.ceil(64 * sc)))
+        # independent implementation of the same antialiased Keys(-0.5) resampling (PIL, float32): equal away from the border
+        P = np.asarray(Image.fromarray(A.astype(np.float32), mode="F").resize((B.shape[1], B.shape[0]), Image.BICUBIC), dtype=np.float64)
+        assert np.abs(B - P)[3:-3, 3:-3].max() < 1e-3
+    R = np.add.outer(np.arange(20.0), 2 * np.arange(30.0))
+    U = c.imresize(R, 2)                                                                            # cubic convolution reproduces ramps
+    assert abs((U[10, 11] - U[10, 10]) - 1.0) < 1e-12 and abs((U[11, 10] - U[10, 10]) - 0.5) < 1e-12
+    assert c.imresize(np.zeros((33, 47, 2)), size=(17, 24)).shape == (17, 24, 2)
+    V = np.arange(12.0).reshape(3, 4)
+    q = c.interp2_linear(V, np.array([[1.5, 4.0, 4.1, 0.99]]), np.array([[1.0, 3.0, 2.0, 1.0]]))
+    assert q[0, 0] == 0.5 and q[0, 1] == 11.0 and np.isnan(q[0, 2]) and np.isnan(q[0, 3])
+    F = np.array([[1, np.nan, np.nan, np.nan, 5.0], [np.nan] * 5, [np.nan, 2, np.nan, np.nan, np.nan]])
+    assert np.array_equal(c.fillmissing_nearest(F, 1)[0], [1, 1, 5, 5, 5]) and np.isnan(c.fillmissing_nearest(F, 1)[1]).all()
+    G = c.fillmissing_nearest(c.fillmissing_nearest(F, 0), 1)
+    assert not np.isnan(G).any() and np.array_equal(G[1], [1, 2, 2, 5, 5])
+    o = c.ctf_options(dict(K=11, its=3000, epsn=1e-6, lambdas=5, lambdad=1), np.dstack([np.full((4, 4), -2.0), np.full((4, 4), 3.0)]))
+    assert (o["L"], o["step0"], o["sigma_step_scale"], o["sigma_max"], o["corr_tor"], o["minu"], o["maxv"]) == (1, 0.07, 0.3, 25.0, 0.999, -2.0, 3.0)
+
+
+def test_ctf_pyramid_glue_is_consistent(pkg, monkeypatch):
+    """The pyramid loop of legacy/optical_flow_ctf.m:21-36 with the per-level solver replaced by one that returns the exact
+    residual flow: resizing, x2 scaling, warp sign (I1_w(x) = I1(x - warp)) and accumulation must then reproduce the ground truth,
+    and the warped first frame must match the second frame at every level (no GPU involved)."""
+    c = pkg.ctf
+    M, N = 96, 128
+    I1, I2, flow, _ = pkg.synthetic_pair(M, N, seed=3, flow_scale=2.0)
+    seen = []
+
+    def perfect(options, I1w, I2l, GRDT, seed=0, device=-1, aepe_target=None):
+        m, n = I1w.shape
+        seen.append((float(np.abs(I1w - I2l)[4:-4, 4:-4].mean()), float(np.abs(aepe_target).max())))
+        assert GRDT.shape == (M, N, 2)                                                     # :31 passes trueFlow.*scale, full size
+        return aepe_target.copy(), np.ones((m, n, 2)), np.zeros((m, n, 2, 2)), np.full(3, np.nan), np.ones(3)
+    monkeypatch.setattr(c, "gqmap_ctf", perfect)
+    warp, levels = c.optical_flow_ctf(I1, I2, flow, dict(K=3, its=3), scales=(1 / 4, 1 / 2, 1))
+    assert np.abs(warp - flow).max() < 1e-9 and all(lv["aepe_after"] < 1e-9 for lv in levels)
+    # level 1 starts from zero warp (photometric error of the raw pair), later levels from the up-scaled previous flow: the warped
+    # frame is then close to the second frame (what remains is the blur of the bilinear warp on this fine texture) and the
+    # residual flow is a fraction of a pixel
+    assert seen[1][0] < 0.6 * seen[0][0] and seen[2][0] < 0.6 * seen[0][0], seen
+    assert seen[1][1] < 0.5 and seen[2][1] < 0.5, seen
+    x, y = np.meshgrid(np.arange(1, N + 1.0), np.arange(1, M + 1.0))
+    right = np.nanmean(np.abs(c.interp2_linear(I1, x - flow[:, :, 0], y - flow[:, :, 1]) - I2)[6:-6, 6:-6])
+    wrong = np.nanmean(np.abs(c.interp2_linear(I1, x + flow[:, :, 0], y + flow[:, :, 1]) - I2)[6:-6, 6:-6])
+    assert right < 0.4 * wrong                                                              # sign of the warp (:28-29)
