@@ -65,6 +65,8 @@ SIGNATURES = {
     "qgmap_aepe": (C.c_int, [C.c_void_p, _DP, _DP, _U8P, _DP]),
     "qgmap_solve": (C.c_int, [C.POINTER(QgmapConfig), _DP, _DP, C.c_int, C.c_int, C.c_int, C.POINTER(_DP), C.c_uint64,
                               _DP, _U8P, _DP, _DP, _DP, _DP, _DP, _DP, _IP]),
+    "qgmap_group_solve": (C.c_int, [C.POINTER(QgmapConfig), _DP, _DP, C.c_int, C.c_int, C.c_int, C.c_int, _IP, C.POINTER(_DP), C.c_uint64,
+                                    _DP, _U8P, _DP, _DP, _DP, _DP, _DP, _DP, _IP]),
     "qgmap_last_solve_stats": (C.c_int, [C.POINTER(C.c_longlong), C.POINTER(C.c_float)]),
     "qgmap_find_map": (C.c_int, [_DP] * 5 + [C.c_int, C.c_int, C.c_int, _DP, C.c_int]),
     "qgmap_flow_to_color": (C.c_int, [_DP, C.c_int, C.c_int, C.c_double, _U8P, _DP, _DP, _U8P]),

@@ -298,7 +298,11 @@ static int import_planes(qgmap_handle *h, const double *src, int planes, int pla
     const size_t n = (size_t)h->M * h->N * planes;
     int rc = ensure_stage(h, n);
     if (rc) return rc;
-    QG_CUDA(h, cudaMemcpyAsync(h->stage, src, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (h->g0 == 0 && h->g1 == h->M)
+        QG_CUDA(h, cudaMemcpyAsync(h->stage, src, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    else      // a band needs only its stored rows [g0,g1) of every column: strided copy (column-major source)
+        QG_CUDA(h, cudaMemcpy2DAsync(h->stage + h->g0, (size_t)h->M * sizeof(double), src + h->g0, (size_t)h->M * sizeof(double),
+                                     (size_t)(h->g1 - h->g0) * sizeof(double), (size_t)h->N * planes, cudaMemcpyHostToDevice, h->stream));
     dim3 tb(32, 8), tg((h->N + 31) / 32, (h->rows_local + 31) / 32, planes);
     for (int b = 0; b < 2; ++b)
         qgmap_import_kernel<float><<<tg, tb, 0, h->stream>>>(h->stage, h->M, h->N, planes,
@@ -316,12 +320,15 @@ static int export_planes(qgmap_handle *h, int cur, int planes, int plane_first, 
     int rc = ensure_stage(h, n);
     if (rc) return rc;
     const bool whole = (h->row_begin == 0 && h->row_end == h->M);
-    if (!whole) QG_CUDA(h, cudaMemcpyAsync(h->stage, dst, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     dim3 tb(32, 8), tg((h->N + 31) / 32, (h->row_end - h->row_begin + 31) / 32, planes);
     qgmap_export_kernel<float><<<tg, tb, 0, h->stream>>>(h->buf[cur] + (size_t)plane_first * h->plane, h->P, h->plane, h->g0,
                                                           h->row_begin, h->row_end, h->stage, h->M, h->N);
     QG_CUDA(h, cudaGetLastError());
-    QG_CUDA(h, cudaMemcpyAsync(dst, h->stage, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (whole)
+        QG_CUDA(h, cudaMemcpyAsync(dst, h->stage, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    else      // a band returns only the rows it owns: strided copy into the caller's full-grid array, other rows untouched
+        QG_CUDA(h, cudaMemcpy2DAsync(dst + h->row_begin, (size_t)h->M * sizeof(double), h->stage + h->row_begin, (size_t)h->M * sizeof(double),
+                                     (size_t)(h->row_end - h->row_begin) * sizeof(double), (size_t)h->N * planes, cudaMemcpyDeviceToHost, h->stream));
     QG_CUDA(h, cudaStreamSynchronize(h->stream));
     return QGMAP_OK;
 }
@@ -393,18 +400,26 @@ struct Rng {
     double uniform() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
 };
 
-extern "C" int qgmap_init_state(qgmap_handle *h, uint64_t seed)
+// gqmap_gpu_mixture.m:18-24 with the library's own generator (MATLAB's rand stream is not reproducible outside MATLAB)
+void qgmap_random_state(const qgmap_config &c, size_t n, int L, uint64_t seed, std::vector<double> &w, std::vector<double> &muu,
+                        std::vector<double> &muv, std::vector<double> &sigu, std::vector<double> &sigv)
 {
-    if (!h) return QGMAP_ERR_ARG;
-    const size_t n = (size_t)h->M * h->N * h->L;
-    const qgmap_config &c = h->cfg;
-    std::vector<double> w(h->L), muu(n), muv(n), sigu(n), sigv(n), pn(n, 0.0), rou(n * 4, 0.0);
+    w.resize(L); muu.resize(n); muv.resize(n); sigu.resize(n); sigv.resize(n);
     Rng r(seed);
     for (auto &v : w) v = r.uniform();                                           // :18
     for (auto &v : muu) v = c.minu + r.uniform() * (c.maxu - c.minu);            // :19
     for (auto &v : muv) v = c.minv + r.uniform() * (c.maxv - c.minv);            // :20
     for (auto &v : sigu) v = r.uniform() + (c.maxu - c.minu);                    // :21
     for (auto &v : sigv) v = r.uniform() + (c.maxv - c.minv);                    // :22
+}
+
+extern "C" int qgmap_init_state(qgmap_handle *h, uint64_t seed)
+{
+    if (!h) return QGMAP_ERR_ARG;
+    const size_t n = (size_t)h->M * h->N * h->L;
+    const qgmap_config &c = h->cfg;
+    std::vector<double> w, muu, muv, sigu, sigv, pn(n, 0.0), rou(n * 4, 0.0);
+    qgmap_random_state(c, n, h->L, seed, w, muu, muv, sigu, sigv);
     return qgmap_set_state(h, muu.data(), muv.data(), sigu.data(), sigv.data(), pn.data(), rou.data(), w.data(), nullptr,
                            c.temperature, 1);
 }
@@ -864,6 +879,70 @@ extern "C" int qgmap_solve(const qgmap_config *cfg, const double *I1, const doub
     if (alpha) std::copy(a.begin(), a.end(), alpha);
     g_solve_launches = launches; g_solve_ms = ms;
     qgmap_destroy(h);
+    return QGMAP_OK;
+}
+
+// gqmap_gpu_mixture(options,I1,I2) with options.devices: the loop of qgmap_solve over a band group
+extern "C" int qgmap_group_solve(const qgmap_config *cfg, const double *I1, const double *I2, int Mo, int No, int its,
+                                 int nbands, const int *devices,
+                                 const double *const *init, uint64_t seed, const double *tflow, const uint8_t *unknown,
+                                 double *mu, double *sigma, double *alpha, double *AEPE, double *Energy, double *logP,
+                                 int *its_done)
+{
+    qgmap_handle *nh = nullptr;
+    if (its < 1 || nbands < 1) QG_FAIL(nh, QGMAP_ERR_ARG, "qgmap_group_solve: its=%d nbands=%d", its, nbands);
+    qgmap_group *g = nullptr;
+    int rc = qgmap_group_create(cfg, I1, I2, Mo, No, nbands, devices, &g);
+    if (rc) return rc;
+    auto bail = [&](int code) { qgmap_group_destroy(g); return code; };
+    if (init) rc = qgmap_group_set_state(g, init[0], init[1], init[2], init[3], init[4], init[5], init[6], nullptr, cfg->temperature, 1);
+    else rc = qgmap_group_init_state(g, seed);
+    if (rc) return bail(rc);
+    int M = 0, N = 0, L = 0;
+    qgmap_group_dims(g, &M, &N, &L, nullptr);
+    const size_t n3 = (size_t)M * N * L;
+    std::vector<double> mu_tmp, sg_tmp, al(L), map((size_t)M * N * 2);
+    if (!mu) { mu_tmp.resize(2 * n3); mu = mu_tmp.data(); }
+    if (!sigma) { sg_tmp.resize(2 * n3); sigma = sg_tmp.data(); }
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    for (int i = 0; i < its; ++i) {
+        if (AEPE) AEPE[i] = nan;
+        if (Energy) Energy[i] = 0.0;
+        if (logP) logP[i] = nan;
+    }
+    qgmap_handle *h0 = qgmap_group_band(g, 0);                                       // monitoring kernels run on band 0's device
+    const int every = cfg->log_every > 0 ? cfg->log_every : 300;
+    int it = 1, stopped = 0;
+    float ms = 0.f;
+    while (!stopped && it <= its) {
+        const int next_mon = (it == 1) ? 1 : ((it + every - 1) / every) * every;
+        const int n = std::min(next_mon, its) - it + 1;
+        int done = 0;
+        rc = qgmap_group_step(g, n, its, Energy ? Energy + (it - 1) : nullptr, nullptr, nullptr, &done, &stopped);
+        if (rc) return bail(rc);
+        float m1 = 0.f;
+        qgmap_group_last_step_ms(g, &m1);
+        ms += m1;
+        it += done;
+        const int last = it - 1;
+        if (done > 0 && (last == 1 || last % every == 0) && (AEPE || logP || !g_dump_dir.empty())) {     // :52-68
+            rc = qgmap_group_get_state(g, mu, mu + n3, sigma, sigma + n3, nullptr, nullptr, nullptr, al.data(), nullptr, nullptr);
+            if (rc) return bail(rc);
+            if ((rc = qgmap_find_map(al.data(), mu, sigma, mu + n3, sigma + n3, M, N, L, map.data(), h0->device)) != QGMAP_OK) return bail(rc);
+            double lp = nan;
+            if ((rc = qgmap_logp(h0, map.data(), &lp)) != QGMAP_OK) { g_last_error = h0->err; return bail(rc); }   // also stages the map on h0
+            if (logP) logP[last - 1] = lp;
+            if (!g_dump_dir.empty() && (rc = dump_map_png(h0, last)) != QGMAP_OK) { g_last_error = h0->err; return bail(rc); }
+            if (tflow && AEPE && (rc = qgmap_aepe(h0, map.data(), tflow, unknown, &AEPE[last - 1])) != QGMAP_OK) { g_last_error = h0->err; return bail(rc); }
+        }
+        if (done < n) break;
+    }
+    if (its_done) *its_done = it - 1;
+    rc = qgmap_group_get_state(g, mu, mu + n3, sigma, sigma + n3, nullptr, nullptr, nullptr, al.data(), nullptr, nullptr);   // :183-185
+    if (rc) return bail(rc);
+    if (alpha) std::copy(al.begin(), al.end(), alpha);
+    g_solve_launches = 0; g_solve_ms = ms;
+    qgmap_group_destroy(g);
     return QGMAP_OK;
 }
 

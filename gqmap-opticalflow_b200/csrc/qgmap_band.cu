@@ -189,6 +189,8 @@ __global__ void qgmap_group_advance_kernel(const __grid_constant__ QgIterParams 
     qg_advance(p, p.ctrl, tot);
 }
 
+qgmap_handle *qgmap_group_band(qgmap_group *g, int b) { return g->bands[b]; }
+
 extern "C" int qgmap_group_destroy(qgmap_group *g)
 {
     if (!g) return QGMAP_ERR_ARG;
@@ -294,11 +296,12 @@ extern "C" int qgmap_group_set_state(qgmap_group *g, const double *muu, const do
 extern "C" int qgmap_group_init_state(qgmap_group *g, uint64_t seed)
 {
     if (!g) return QGMAP_ERR_ARG;
-    for (qgmap_handle *h : g->bands) {           // every band draws the same full-grid arrays and keeps its rows
-        int rc = qgmap_init_state(h, seed);
-        if (rc) { g->err = h->err; return rc; }
-    }
-    return QGMAP_OK;
+    qgmap_handle *h0 = g->bands[0];              // the full-grid arrays are drawn once; every band keeps its rows
+    const size_t n = (size_t)g->M * g->N * g->L;
+    std::vector<double> w, muu, muv, sigu, sigv, pn(n, 0.0), rou(n * 4, 0.0);
+    qgmap_random_state(h0->cfg, n, g->L, seed, w, muu, muv, sigu, sigv);
+    return qgmap_group_set_state(g, muu.data(), muv.data(), sigu.data(), sigv.data(), pn.data(), rou.data(), w.data(), nullptr,
+                                 h0->cfg.temperature, 1);
 }
 
 extern "C" int qgmap_group_get_state(qgmap_group *g, double *muu, double *muv, double *sigu, double *sigv, double *pn, double *rou,

@@ -78,6 +78,11 @@ int qgmap_p2p_iteration(qgmap_handle *h, long long *launches);  // iteration ker
 int qgmap_prepare_step(qgmap_handle *h, int n, int its);
 int qgmap_finish_step(qgmap_handle *h, double *energy, double *ptdmu, double *ptdsigma, int *n_done, int *stopped);
 void qgmap_set_last_error(const char *msg);
+#include <vector>
+void qgmap_random_state(const qgmap_config &c, size_t n, int L, uint64_t seed, std::vector<double> &w, std::vector<double> &muu,
+                        std::vector<double> &muv, std::vector<double> &sigu, std::vector<double> &sigv);
+struct qgmap_group;
+qgmap_handle *qgmap_group_band(qgmap_group *g, int b);           // band b's handle (monitoring kernels of qgmap_group_solve)
 
 extern thread_local long long g_solve_launches;
 extern thread_local float g_solve_ms;

@@ -14,7 +14,7 @@ wrappers in matlab/ and the MEX gateways in mex/ bind the very same C symbols.
 `options` is a dict (or any object with attributes) carrying the reference's fields (gqmap_gpu_mixture.m:3-6):
 trueFlow, unknownIdx, its, K, L, temperature, drate, epsn, lambdad, lambdas, minu, maxu, minv, maxv [, dir].
 New OPTIONAL fields only: init (dict of the 7 state arrays muu,muv,sigmau,sigmav,pn,rou,w), seed, alpha_mode
-('softmax'|'projsplx'), device, log_every.  options.dir, when given, receives <it>.png at every monitored iteration
+('softmax'|'projsplx'), device, devices (list of CUDA ordinals: the frame pair is split into one row band per entry), log_every.  options.dir, when given, receives <it>.png at every monitored iteration
 (:59-62); the directory must exist (the drivers mkdir it, optical_flow.m:25).  Everything runs on the GPU; there is no CPU path.
 """
 import ctypes as C
@@ -114,10 +114,17 @@ def _solve(options, I1, I2, variant):
     done = C.c_int(0)
     out_dir = _opt(options, "dir")                  # gqmap_gpu_mixture.m:62: [options.dir '/' num2str(it) '.png']
     check(lib.qgmap_solve_set_dump_dir(None if not out_dir else str(out_dir).encode()))
+    devices = _opt(options, "devices")             # new optional field: one row band of the frame pair per listed CUDA device
     try:
-        check(lib.qgmap_solve(C.byref(cfg), dptr(I1), dptr(I2), Mo, No, its, init_arr,
-                              C.c_uint64(int(_opt(options, "seed", 0))), dptr(tflow), u8ptr(unk),
-                              dptr(mu), dptr(sigma), dptr(alpha), dptr(AEPE), dptr(Energy), dptr(logP), C.byref(done)))
+        if devices is not None and len(devices) > 1:
+            dev = (C.c_int * len(devices))(*[int(d) for d in devices])
+            check(lib.qgmap_group_solve(C.byref(cfg), dptr(I1), dptr(I2), Mo, No, its, len(devices), dev, init_arr,
+                                        C.c_uint64(int(_opt(options, "seed", 0))), dptr(tflow), u8ptr(unk),
+                                        dptr(mu), dptr(sigma), dptr(alpha), dptr(AEPE), dptr(Energy), dptr(logP), C.byref(done)))
+        else:
+            check(lib.qgmap_solve(C.byref(cfg), dptr(I1), dptr(I2), Mo, No, its, init_arr,
+                                  C.c_uint64(int(_opt(options, "seed", 0))), dptr(tflow), u8ptr(unk),
+                                  dptr(mu), dptr(sigma), dptr(alpha), dptr(AEPE), dptr(Energy), dptr(logP), C.byref(done)))
     finally:
         lib.qgmap_solve_set_dump_dir(None)
     return mu, sigma, alpha.reshape(1, 1, L), AEPE.reshape(its, 1), Energy.reshape(its, 1), logP.reshape(its, 1)

@@ -4,7 +4,9 @@ function [mu, sigma, alpha, AEPE, Energy, logP] = gqmap_gpu_mixture(options, I1,
 %   temperature, drate, epsn, lambdad, lambdas, minu, maxu, minv, maxv), same six outputs with the same shapes
 %   (mu,sigma: M x N x L x 2; alpha: 1 x 1 x L; AEPE,Energy,logP: its x 1, prefilled NaN/0/NaN).
 %   New OPTIONAL fields: options.init (struct muu,muv,sigmau,sigmav,pn,rou,w), options.seed, options.alpha_mode
-%   ('softmax' | 'projsplx'), options.device, options.log_every, options.verbose.
+%   ('softmax' | 'projsplx'), options.device, options.devices (vector of CUDA ordinals: the frame pair is split into one row band
+%   per GPU, boundary rows exchanged over NVLink by the library), options.log_every, options.verbose; options.dir, when present,
+%   receives <it>.png at every monitored iteration exactly as in the reference (:59-62).
 %   The whole loop (gradients, update, Energy, alpha update, MAP/AEPE/logP monitoring every 300 iterations) runs on the
 %   GPU inside one MEX call; with options.verbose the loop is driven from MATLAB in chunks so progress can be printed.
 if isfield(options, 'verbose') && options.verbose

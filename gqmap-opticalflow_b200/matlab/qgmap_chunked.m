@@ -21,7 +21,7 @@ while ~stopped && it <= its
         end
         logP(last) = gqmap_mex('logp', h, map); mark = last;
         if isfield(options,'dir') && ~isempty(options.dir)
-            if variant == 1, flc = flowToColor_mex(repelem(map,4,4)); flc = flc(5:end-4,5:end-4,:);
+            if variant == 1, flow = repelem(map,4,4); flc = flowToColor_mex(flow(5:end-4,5:end-4,:));
             else, flc = flowToColor_mex(map); end
             imwrite(flc, [options.dir, '/', num2str(last), '.png']);
         end

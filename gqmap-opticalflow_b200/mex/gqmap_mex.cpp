@@ -63,10 +63,31 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
         mxArray *al = mxCreateNumericArray(3, d3, mxDOUBLE_CLASS, mxREAL);
         mxArray *ae = mxCreateDoubleMatrix(its, 1, mxREAL), *en = mxCreateDoubleMatrix(its, 1, mxREAL), *lp = mxCreateDoubleMatrix(its, 1, mxREAL);
         int done = 0;
-        qg_check(qgmap_solve(&cfg, I1, I2, Mo, No, its, have_init ? init : NULL, (uint64_t)qg_field(prhs[2], "seed", 0, 0),
-                             tf && !mxIsEmpty(tf) ? mxGetPr(tf) : NULL,
-                             uk && !mxIsEmpty(uk) ? (const uint8_t *)mxGetLogicals(uk) : NULL,
-                             mxGetPr(mu), mxGetPr(sg), mxGetPr(al), mxGetPr(ae), mxGetPr(en), mxGetPr(lp), &done), NULL);
+        /* options.dir (gqmap_gpu_mixture.m:62): <dir>/<it>.png at every monitored iteration */
+        const mxArray *dir = mxGetField(prhs[2], 0, "dir");
+        char *dirs = (dir && mxIsChar(dir) && !mxIsEmpty(dir)) ? mxArrayToString(dir) : NULL;
+        qgmap_solve_set_dump_dir(dirs);
+        if (dirs) mxFree(dirs);
+        /* options.devices (new, optional): one row band of the frame pair per listed GPU */
+        const mxArray *dv = mxGetField(prhs[2], 0, "devices");
+        int devs[QGMAP_P2P_RANKS_MAX], ndev = 0;
+        if (dv && mxIsDouble(dv)) {
+            ndev = (int)mxGetNumberOfElements(dv);
+            if (ndev > QGMAP_P2P_RANKS_MAX) mexErrMsgIdAndTxt("qgmap:arg", "options.devices lists more than %d devices.", QGMAP_P2P_RANKS_MAX);
+            for (int k = 0; k < ndev; ++k) devs[k] = (int)mxGetPr(dv)[k];
+        }
+        const double *tfp = tf && !mxIsEmpty(tf) ? mxGetPr(tf) : NULL;
+        const uint8_t *ukp = uk && !mxIsEmpty(uk) ? (const uint8_t *)mxGetLogicals(uk) : NULL;
+        const uint64_t seed = (uint64_t)qg_field(prhs[2], "seed", 0, 0);
+        int rc;
+        if (ndev > 1)
+            rc = qgmap_group_solve(&cfg, I1, I2, Mo, No, its, ndev, devs, have_init ? init : NULL, seed, tfp, ukp,
+                                   mxGetPr(mu), mxGetPr(sg), mxGetPr(al), mxGetPr(ae), mxGetPr(en), mxGetPr(lp), &done);
+        else
+            rc = qgmap_solve(&cfg, I1, I2, Mo, No, its, have_init ? init : NULL, seed, tfp, ukp,
+                             mxGetPr(mu), mxGetPr(sg), mxGetPr(al), mxGetPr(ae), mxGetPr(en), mxGetPr(lp), &done);
+        qgmap_solve_set_dump_dir(NULL);
+        qg_check(rc, NULL);
         mxArray *outs[6] = {mu, sg, al, ae, en, lp};
         for (int k = 0; k < 6 && (k == 0 || k < nlhs); ++k) plhs[k] = outs[k];
     } else if (!strcmp(c, "create")) {

@@ -135,6 +135,16 @@ int qgmap_solve(const qgmap_config *cfg, const double *I1, const double *I2, int
                 double *mu, double *sigma, double *alpha, double *AEPE, double *Energy, double *logP,
                 int *its_done);
 
+/* The same one-call solver with the frame pair split into `nbands` row bands, band b on devices[b] (options.devices of the
+ * MATLAB-level call; NULL: all bands on the current device): qgmap_group_* underneath -- peer-memory exchange kernel when
+ * every band has its own GPU -- and the reference's monitoring cadence (MAP of the gathered beliefs via qgmap_find_map,
+ * AEPE / logP on band 0's device, PNG dumps).  Beliefs are bit-identical to qgmap_solve's. */
+int qgmap_group_solve(const qgmap_config *cfg, const double *I1, const double *I2, int Mo, int No, int its,
+                      int nbands, const int *devices,
+                      const double *const *init, uint64_t seed, const double *tflow, const uint8_t *unknown,
+                      double *mu, double *sigma, double *alpha, double *AEPE, double *Energy, double *logP,
+                      int *its_done);
+
 /* Kernels launched / device ms (CUDA events) of the last qgmap_solve on this thread. */
 int qgmap_last_solve_stats(long long *launches, float *kernel_ms);
 

@@ -52,3 +52,28 @@ def test_band_group_stop_rule(pkg, O):
         r = g.step(10, its=6)
         assert (r["n_done"], r["stopped"]) == (6, True)
         assert g.step(3, its=6)["n_done"] == 0
+
+
+@pytest.mark.parametrize("variant", ["full", "super"])
+def test_solve_with_options_devices_matches_single_domain(pkg, O, variant, tmp_path):
+    """gqmap_gpu_mixture(options,I1,I2) with the new optional options.devices (one row band per entry; here three bands that share
+    the GPU) returns the same beliefs bit for bit and the same AEPE / Energy / logP histories as the undivided call, PNG dumps
+    included."""
+    sup = variant == "super"
+    Mo, No = (96, 128) if sup else (60, 72)
+    I1, I2, flow, (minu, maxu, minv, maxv) = pkg.synthetic_pair(Mo, No)
+    opts = dict(K=3, L=2, its=13, temperature=0.2 if sup else 0.0, drate=0.75, epsn=1e-6, lambdad=1.0, lambdas=5.0, minu=minu, maxu=maxu,
+                minv=minv, maxv=maxv, seed=5, log_every=4, trueFlow=flow, unknownIdx=np.zeros((Mo, No), bool), alpha_start=2, alpha_scale=1e-5)
+    fn = pkg.gqmap_gpuSuper_mix_entropy if sup else pkg.gqmap_gpu_mixture
+    (tmp_path / "a").mkdir(); (tmp_path / "b").mkdir()
+    a = fn(dict(opts, dir=str(tmp_path / "a")), I1, I2)
+    b = fn(dict(opts, dir=str(tmp_path / "b"), devices=[0, 0, 0]), I1, I2)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])                       # mu, sigma
+    assert np.abs(a[2] - b[2]).max() < 1e-14                                               # alpha
+    for k in (3, 4, 5):                                                                    # AEPE, Energy, logP (NaN pattern included)
+        assert np.array_equal(np.isnan(a[k]), np.isnan(b[k]))
+        m = ~np.isnan(a[k])
+        assert np.abs(b[k][m] / a[k][m] - 1).max() < 1e-11, k
+    assert sorted(p.name for p in (tmp_path / "b").iterdir()) == ["1.png", "12.png", "4.png", "8.png"]
+    for p in (tmp_path / "a").iterdir():
+        assert p.read_bytes() == (tmp_path / "b" / p.name).read_bytes()

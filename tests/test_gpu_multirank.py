@@ -51,3 +51,26 @@ def test_group_one_band_per_gpu_is_bit_identical():
             assert np.array_equal(a[f], b[f]), (variant, f)
         E = np.concatenate([ra["Energy"], rb["Energy"]])
         assert np.abs(E / r1["Energy"] - 1).max() < 1e-12 and np.abs(a["alpha"] - b["alpha"]).max() < 1e-14
+
+
+@pytest.mark.gpu
+def test_solve_with_options_devices_on_distinct_gpus():
+    """The reference-facing call with options.devices = [0,1,...]: one band per GPU, peer-memory exchange kernel underneath."""
+    import importlib
+    import numpy as np
+    import torch
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, ROOT)
+    pkg = importlib.import_module("gqmap-opticalflow_b200")
+    Mo, No = 96, 120
+    I1, I2, flow, (minu, maxu, minv, maxv) = pkg.synthetic_pair(Mo, No)
+    opts = dict(K=5, L=3, its=25, temperature=0.0, drate=0.5, epsn=1e-6, lambdad=1.0, lambdas=5.0, minu=minu, maxu=maxu, minv=minv,
+                maxv=maxv, seed=5, log_every=10, trueFlow=flow, unknownIdx=np.zeros((Mo, No), bool), alpha_start=2, alpha_scale=1e-5)
+    a = pkg.gqmap_gpu_mixture(opts, I1, I2)
+    b = pkg.gqmap_gpu_mixture(dict(opts, devices=list(range(min(ndev, 4)))), I1, I2)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.abs(a[2] - b[2]).max() < 1e-14
+    for k in (3, 4, 5):
+        m = ~np.isnan(a[k])
+        assert np.array_equal(np.isnan(a[k]), np.isnan(b[k])) and np.abs(b[k][m] / a[k][m] - 1).max() < 1e-11
