@@ -647,13 +647,12 @@ static int map_device(qgmap_handle *h)
 {
     int rc = ensure_map(h);
     if (rc) return rc;
-    if (h->nranks > 1) QG_FAIL(h, QGMAP_ERR_STATE, "qgmap_get_map on a band handle: gather the state and use qgmap_find_map");
     const int cur = (h->ctrl_host->it - 1) & 1;
     const float *b = h->buf[cur];
     const long long fs = (long long)h->L * h->plane;
     const long long tot = 2LL * h->M * h->N;
     qgmap_launch_find_map_f32(&h->ctrl->alpha[0], b + F_MUU * fs, b + F_SIGU * fs, b + F_MUV * fs, b + F_SIGV * fs, h->plane,
-                              h->M, h->N, h->L, h->P, h->g0, h->d_map, tot, h->stream);
+                              h->M, h->N, h->L, h->P, h->g0, h->row_begin, h->row_end, h->d_map, tot, h->stream);
     QG_CUDA(h, cudaGetLastError());
     return QGMAP_OK;
 }
@@ -666,7 +665,11 @@ extern "C" int qgmap_get_map(qgmap_handle *h, double *map)
     int rc = sync_ctrl(h);
     if (rc) return rc;
     if ((rc = map_device(h)) != QGMAP_OK) return rc;
-    QG_CUDA(h, cudaMemcpyAsync(map, h->d_map, (size_t)h->M * h->N * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (h->row_begin == 0 && h->row_end == h->M)
+        QG_CUDA(h, cudaMemcpyAsync(map, h->d_map, (size_t)h->M * h->N * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    else      // a band fills only the rows it owns (like qgmap_get_state)
+        QG_CUDA(h, cudaMemcpy2DAsync(map + h->row_begin, (size_t)h->M * sizeof(double), h->d_map + h->row_begin, (size_t)h->M * sizeof(double),
+                                     (size_t)(h->row_end - h->row_begin) * sizeof(double), (size_t)h->N * 2, cudaMemcpyDeviceToHost, h->stream));
     QG_CUDA(h, cudaStreamSynchronize(h->stream));
     return QGMAP_OK;
 }
@@ -926,9 +929,10 @@ extern "C" int qgmap_group_solve(const qgmap_config *cfg, const double *I1, cons
         it += done;
         const int last = it - 1;
         if (done > 0 && (last == 1 || last % every == 0) && (AEPE || logP || !g_dump_dir.empty())) {     // :52-68
-            rc = qgmap_group_get_state(g, mu, mu + n3, sigma, sigma + n3, nullptr, nullptr, nullptr, al.data(), nullptr, nullptr);
-            if (rc) return bail(rc);
-            if ((rc = qgmap_find_map(al.data(), mu, sigma, mu + n3, sigma + n3, M, N, L, map.data(), h0->device)) != QGMAP_OK) return bail(rc);
+            for (int b = 0; b < nbands; ++b) {                                                       // every band extracts the MAP of its
+                qgmap_handle *hb = qgmap_group_band(g, b);                                           // own rows on its own GPU (:52-58)
+                if ((rc = qgmap_get_map(hb, map.data())) != QGMAP_OK) { g_last_error = hb->err; return bail(rc); }
+            }
             double lp = nan;
             if ((rc = qgmap_logp(h0, map.data(), &lp)) != QGMAP_OK) { g_last_error = h0->err; return bail(rc); }   // also stages the map on h0
             if (logP) logP[last - 1] = lp;

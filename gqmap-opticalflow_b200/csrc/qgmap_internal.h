@@ -54,7 +54,7 @@ struct qgmap_handle {
 // qgmap_map.cu (compiled with -fmad=false: fp64 monitoring arithmetic must not be contracted)
 void qgmap_launch_find_map_f32(const double *alpha, const float *mu_u, const float *sig_u, const float *mu_v,
                                const float *sig_v, long long comp_stride, int M, int N, int L, int pitch, int row_off,
-                               double *map, long long total, cudaStream_t s);
+                               int r0, int r1, double *map, long long total, cudaStream_t s);
 void qgmap_launch_find_map_f64(const double *alpha, const double *mu_u, const double *sig_u, const double *mu_v,
                                const double *sig_v, long long comp_stride, int M, int N, int L, double *map,
                                long long total, cudaStream_t s);

@@ -5,11 +5,11 @@
 
 void qgmap_launch_find_map_f32(const double *alpha, const float *mu_u, const float *sig_u, const float *mu_v,
                                const float *sig_v, long long comp_stride, int M, int N, int L, int pitch, int row_off,
-                               double *map, long long total, cudaStream_t s)
+                               int r0, int r1, double *map, long long total, cudaStream_t s)
 {
     const int tb = 128;
     qgmap_find_map_kernel<float><<<(unsigned)((total + tb - 1) / tb), tb, 0, s>>>(alpha, mu_u, sig_u, mu_v, sig_v, comp_stride,
-                                                                                   M, N, L, 1, pitch, row_off, map);
+                                                                                   M, N, L, 1, pitch, row_off, r0, r1, map);
 }
 void qgmap_launch_find_map_f64(const double *alpha, const double *mu_u, const double *sig_u, const double *mu_v,
                                const double *sig_v, long long comp_stride, int M, int N, int L, double *map,
@@ -17,7 +17,7 @@ void qgmap_launch_find_map_f64(const double *alpha, const double *mu_u, const do
 {
     const int tb = 128;
     qgmap_find_map_kernel<double><<<(unsigned)((total + tb - 1) / tb), tb, 0, s>>>(alpha, mu_u, sig_u, mu_v, sig_v, comp_stride,
-                                                                                    M, N, L, 0, 0, 0, map);
+                                                                                    M, N, L, 0, 0, 0, 0, M, map);
 }
 static QgMonParams conv(const QgMonArgs &a)
 {

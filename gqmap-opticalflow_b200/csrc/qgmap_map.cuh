@@ -91,7 +91,7 @@ template <typename TIn>
 __global__ void qgmap_find_map_kernel(const double *__restrict__ alpha, const TIn *__restrict__ mu_u,
                                       const TIn *__restrict__ sig_u, const TIn *__restrict__ mu_v,
                                       const TIn *__restrict__ sig_v, long long comp_stride, int M, int N, int L,
-                                      int in_row_major, int in_pitch, int row_off, double *__restrict__ map)
+                                      int in_row_major, int in_pitch, int row_off, int r0, int r1, double *__restrict__ map)
 {
     const long long MN = (long long)M * N;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -99,6 +99,7 @@ __global__ void qgmap_find_map_kernel(const double *__restrict__ alpha, const TI
     const int layer = (int)(t / MN);
     const long long pix = t - (long long)layer * MN;           // column-major pixel index: m + M*n
     const int m = (int)(pix % M), n = (int)(pix / M);
+    if (m < r0 || m >= r1) return;                             // a row band extracts the rows it owns
     const long long off = in_row_major ? ((long long)(m - row_off) * in_pitch + n) : pix;
     const TIn *mu = layer ? mu_v : mu_u, *sg = layer ? sig_v : sig_u;
     double a[QG_LMAX], u[QG_LMAX], o[QG_LMAX];

@@ -117,7 +117,7 @@ int qgmap_last_launches(const qgmap_handle *h, long long *launches);
 
 /* MAP flow of the current beliefs: gqmap_gpu_mixture.m:53-58 (L==1: cat(3,mu_u,mu_v); else get_map_mex).
  * map: M x N x 2. */
-int qgmap_get_map(qgmap_handle *h, double *map);
+int qgmap_get_map(qgmap_handle *h, double *map);   /* a row-band handle fills only the rows it owns */
 /* profile_logP(map), gqmap_gpu_mixture.m:148-154 / gqmap_gpuSuper_mix_entropy.m:152-169.  map: M x N x 2. */
 int qgmap_logp(qgmap_handle *h, const double *map, double *lp);
 /* AEPE of a map against ground truth, gqmap_gpu_mixture.m:63-64 / gqmap_gpuSuper_mix_entropy.m:58-63.
