@@ -87,6 +87,16 @@ def test_no_cpu_fallback_without_gpu(pkg):
     assert e.value.status == -2
     with pytest.raises(pkg.QgmapError):
         pkg.Solver(opts, np.zeros((8, 8)), np.zeros((8, 8)))
+    with pytest.raises(pkg.QgmapError) as e:                                   # options.devices -> qgmap_group_solve
+        pkg.gqmap_gpu_mixture(dict(opts, devices=[0, 1]), np.zeros((8, 8)), np.zeros((8, 8)))
+    assert e.value.status == -2
+    with pytest.raises(pkg.QgmapError):
+        pkg.BandGroup(opts, np.zeros((8, 8)), np.zeros((8, 8)), 2)
+    with pytest.raises(pkg.QgmapError):                                        # coarse-to-fine driver: the solver is the CUDA one
+        pkg.optical_flow_ctf(np.zeros((16, 16)), np.zeros((16, 16)), np.zeros((16, 16, 2)), dict(K=3, its=2, epsn=1e-6, lambdas=5, lambdad=1),
+                             scales=(0.5, 1))
+    lib = pkg._lib.lib
+    assert lib.qgmap_band_p2p_export(None, None) == -1 and lib.qgmap_band_p2p_connect(None, 0, 2, None) == -1
 
 
 def test_product_does_not_import_oracle():
