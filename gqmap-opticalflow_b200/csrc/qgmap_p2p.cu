@@ -147,7 +147,7 @@ __global__ void qgmap_p2p_ready_kernel(const __grid_constant__ QgIterParams p, c
         volatile unsigned long long *f = &q.box[q.rank]->flag[threadIdx.x];
         const long long t0 = clock64();
         while (*f < q.gen) {
-            if (clock64() - t0 > 30 * q.timeout_cycles) { sh_bad = 1; break; }
+            if (clock64() - t0 > 12 * q.timeout_cycles) { sh_bad = 1; break; }
             __nanosleep(1000);
         }
     }

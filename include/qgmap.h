@@ -198,7 +198,8 @@ int qgmap_band_connect(qgmap_handle *h, int rank, int nranks, const void *nccl_u
  * advances the control block.  No host involvement, two launches per iteration.  Protocol: every rank calls
  * qgmap_band_p2p_export (fills QGMAP_P2P_BLOB_BYTES), the host all-gathers the blobs (torch.distributed / files), every rank
  * calls qgmap_band_p2p_connect with the nranks blobs in rank order, then a host barrier before the first step.  All ranks must
- * issue the same qgmap_step calls.  A rank that does not hear from a peer within ~10 s stops with QGMAP_ERR_COMM. */
+ * issue the same qgmap_step calls.  A rank that does not hear from a peer within ~10 s (~2 min for the handshake that opens every qgmap_step call) stops with
+ * QGMAP_ERR_COMM; after a re-export every rank must reconnect. */
 #define QGMAP_P2P_BLOB_BYTES 512
 #define QGMAP_P2P_RANKS_MAX 16
 int qgmap_band_p2p_export(qgmap_handle *h, void *blob);
