@@ -20,12 +20,16 @@
 // of 8 warps at 64 registers (+4% K=5, +12% K=3); K >= 7 is FMA-pipe/issue-bound and keeps 3 CTAs of 9 warps at 72 registers.
 // The super-pixel variant has few, heavy beliefs: smaller CTAs, so a straggler warp (border blocks take a slower clamped path)
 // holds back fewer warps at the block reduction.
+#ifndef QG_SMALLK_TH
+#define QG_SMALLK_TH 7
+#define QG_SMALLK_MINB 4
+#endif
 template <int KT, bool SUPER> struct QgTile {
-    static constexpr int TH = SUPER ? 4 : ((KT > 0 && KT <= 5) ? 7 : 8);
-    static constexpr int MINB = SUPER ? 4 : ((KT > 0 && KT <= 5) ? 4 : 3);
+    static constexpr int TH = SUPER ? 4 : ((KT > 0 && KT <= 5) ? QG_SMALLK_TH : 8);
+    static constexpr int MINB = SUPER ? 4 : ((KT > 0 && KT <= 5) ? QG_SMALLK_MINB : 3);
 };
 __host__ __device__ constexpr int qg_tile_rows(int K, bool super) {      // host mirror of QgTile<K,SUPER>::TH (template K set)
-    return super ? 4 : ((K == 3 || K == 5) ? 7 : 8);
+    return super ? 4 : ((K == 3 || K == 5) ? QG_SMALLK_TH : 8);
 }
 #define QG_TH_MAX 8
 #define QG_NRED 4           // block-reduced scalars: energy, dalpha, sum|G_muu|, sum|G_sigu|
