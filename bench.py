@@ -245,8 +245,8 @@ def run_ours(args):
                      "hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"}},
     }
-    if not args.no_cpu:
-        out["cpu_baseline"] = cpu_baseline(pkg, items, budget_s=args.cpu_budget)
+    if not args.no_cpu and world == 1:                 # reported at N=1 only (rank 0's host cores)
+        out["cpu_baseline"] = cpu_baseline(pkg, items, budget_s=args.cpu_budget, nthreads=os.cpu_count() or 1)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -442,7 +442,7 @@ def run_reference(args):
     for i, (name, I1, I2, flow, opts) in enumerate(items):
         M, N = I1.shape
         cfg = O.make_config(M, N, opts["L"], opts["K"], lambdas=opts["lambdas"], minu=opts["minu"], maxu=opts["maxu"],
-                            minv=opts["minv"], maxv=opts["maxv"])
+                            minv=opts["minv"], maxv=opts["maxv"], nthreads=os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1
         probs.append((cfg, I1, O.get_vv(I2), O.init_state(cfg, 4321 + i)))
     px = sum(p[1].size for p in probs)
     it = 1
