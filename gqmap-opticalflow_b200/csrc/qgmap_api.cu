@@ -234,7 +234,8 @@ extern "C" int qgmap_create(const qgmap_config *cfg, const double *I1, const dou
         const long long beliefs = (long long)(N - 2) * std::max(out_rows, 1) * h->L;
         // measured on B200 (profiles/): the 4-lane mapping pays for the super-pixel variant on small grids (1.8x at 120x160 beliefs,
         // K=5); full-resolution it costs ~40% at K=3 where the replicated per-lane prologue/epilogue outweighs the shorter loop
-        h->lanes_per_belief = env ? atoi(env) : ((sup && beliefs < 200000) ? 4 : 1);
+        (void)beliefs;
+        h->lanes_per_belief = env ? atoi(env) : (sup ? 4 : 1);      // super-pixel: 4 lanes win at every size measured (480x640 .. 4K)
         if (h->lanes_per_belief != 4) h->lanes_per_belief = 1;
     }
     const int tw = h->lanes_per_belief == 4 ? QG_CW - 1 : QG_TW - 1;

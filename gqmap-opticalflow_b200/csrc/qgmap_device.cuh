@@ -24,12 +24,16 @@
 #define QG_SMALLK_TH 7
 #define QG_SMALLK_MINB 4
 #endif
+#ifndef QG_SUPER_TH
+#define QG_SUPER_TH 4
+#define QG_SUPER_MINB 4
+#endif
 template <int KT, bool SUPER> struct QgTile {
-    static constexpr int TH = SUPER ? 4 : ((KT > 0 && KT <= 5) ? QG_SMALLK_TH : 8);
-    static constexpr int MINB = SUPER ? 4 : ((KT > 0 && KT <= 5) ? QG_SMALLK_MINB : 3);
+    static constexpr int TH = SUPER ? QG_SUPER_TH : ((KT > 0 && KT <= 5) ? QG_SMALLK_TH : 8);
+    static constexpr int MINB = SUPER ? QG_SUPER_MINB : ((KT > 0 && KT <= 5) ? QG_SMALLK_MINB : 3);
 };
 __host__ __device__ constexpr int qg_tile_rows(int K, bool super) {      // host mirror of QgTile<K,SUPER>::TH (template K set)
-    return super ? 4 : ((K == 3 || K == 5) ? QG_SMALLK_TH : 8);
+    return super ? QG_SUPER_TH : ((K == 3 || K == 5) ? QG_SMALLK_TH : 8);
 }
 #define QG_TH_MAX 8
 #define QG_NRED 4           // block-reduced scalars: energy, dalpha, sum|G_muu|, sum|G_sigu|
