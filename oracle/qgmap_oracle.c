@@ -1,6 +1,6 @@
 /*
  * qgmap_oracle.c -- CPU fp64 restatement of the QGMAP hot path.  TEST INFRASTRUCTURE ONLY
- * (see qgmap_oracle.h: who may load it, and why parity is "unpinned").
+ * (see qgmap_oracle.h: who may load it, which functions are pinned against the reference binaries and which are not).
  *
  * Every function cites the reference file:line it follows (paths relative to the reference root).
  * Compile with -ffp-contract=off so no FMA contraction changes the fp64 arithmetic MATLAB performs.
