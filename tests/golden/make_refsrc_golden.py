@@ -1,0 +1,91 @@
+"""Golden vectors produced by EXECUTING THE REFERENCE'S OWN SOURCE: gqmap_gpu_mixture.m and gqmap_gpuSuper_mix_entropy.m are run,
+unmodified and read from /root/reference, by the mini-MATLAB interpreter oracle/mlab/minimat.py; their MEX calls (get_map_mex,
+flowToColor_mex) go to the reference's own .mexw64 machine code through oracle/refbin.  Run in the build container:
+    python tests/golden/make_refsrc_golden.py        ->  tests/golden/refsrc_<case>.npz   (a few minutes)
+Every file holds the inputs, the `rand` draws the program consumed (so the oracle can start from the same state), the six outputs
+of the solver, the state it does not return (pn, rou, w -- read from the function workspace when it ends) and per-iteration probes
+taken at the solver's own fprintf (state after the update, alpha, T, Energy(it), mean|dmu|, mean|dsigma|)."""
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+REF = "/root/reference"
+
+# name -> (solver file, Mo, No, L, K, T, drate, lambdas, its, iterations to probe, seed)
+CASES = {
+    "full_L2K3":      ("gqmap_gpu_mixture", 8, 9, 2, 3, 0.0, 0.5, 5.0, 4, (1, 2, 3, 4), 11),
+    "full_L1K4":      ("gqmap_gpu_mixture", 7, 8, 1, 4, 0.0, 0.5, 5.0, 3, (1, 2, 3), 12),
+    "full_L3K3_T":    ("gqmap_gpu_mixture", 8, 8, 3, 3, 0.3, 0.5, 5.0, 3, (1, 2, 3), 13),
+    "full_alpha":     ("gqmap_gpu_mixture", 5, 5, 2, 3, 0.0, 0.5, 5.0, 504, (1, 499, 500, 501, 502, 503, 504), 14),
+    "super_L2K3_T":   ("gqmap_gpuSuper_mix_entropy", 16, 20, 2, 3, 0.2, 0.75, 16.0, 3, (1, 2, 3), 15),
+    "super_anneal":   ("gqmap_gpuSuper_mix_entropy", 12, 12, 2, 2, 0.2, 0.75, 16.0, 502, (1, 498, 499, 500, 501, 502), 16),
+}
+RANGE = dict(minu=-3.0, maxu=2.0, minv=-1.5, maxv=4.0)
+PROBE_FIELDS = ("muu", "muv", "sigmau", "sigmav", "pn", "rou", "w", "alpha")
+
+
+def frames(Mo, No, seed):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:Mo, 0:No]
+    I1 = 127 + 60 * np.sin(xx / 2.1) * np.cos(yy / 2.3) + 40 * rng.random((Mo, No))
+    I2 = 127 + 60 * np.sin((xx - 0.8) / 2.1) * np.cos((yy + 0.5) / 2.3) + 40 * rng.random((Mo, No))
+    tflow = rng.normal(0, 1.0, (Mo, No, 2))
+    unk = rng.random((Mo, No)) < 0.05
+    return np.asfortranarray(I1), np.asfortranarray(I2), np.asfortranarray(tflow), np.asfortranarray(unk)
+
+
+def run_case(name, its=None, probes=None):
+    """-> dict of arrays (what the .npz holds)"""
+    from oracle.mlab.minimat import Interp
+    from oracle.refbin import refbin
+    solver, Mo, No, L, K, T, drate, lambdas, its0, probes0, seed = CASES[name]
+    its = its0 if its is None else its
+    probes = probes0 if probes is None else probes
+    I1, I2, tflow, unk = frames(Mo, No, seed)
+    opts = dict(trueFlow=tflow, unknownIdx=unk, its=float(its), K=float(K), L=float(L), temperature=T, drate=drate, epsn=1e-6,
+                lambdad=1.0, lambdas=lambdas, dir="/nonexistent", **RANGE)
+    rng = np.random.default_rng(seed + 1000)
+    draws, snaps = [], {}
+
+    def rand(shape):
+        a = rng.random(int(np.prod(shape))).reshape(shape, order="F")
+        draws.append(np.array(a))
+        return a
+
+    def probe(ws):
+        it = int(ws["it"])
+        if it in probes:
+            d = {f: np.array(np.asarray(ws[f], dtype=np.float64), order="F") for f in PROBE_FIELDS}
+            d.update(T=float(ws["T"]), Energy=float(np.asarray(ws["Energy"]).reshape(-1, order="F")[it - 1]), ptdmu=float(ws["ptdmu"]),
+                     ptdsigma=float(ws["ptdsigma"]), step=float(ws["step"]))
+            snaps[it] = d
+    interp = Interp([REF], rand=rand, on_fprintf=probe,
+                    externals={"get_map_mex": lambda n, *a: (refbin.get_map_mex(*a),),
+                               "flowToColor_mex": lambda n, *a: refbin.flowToColor_mex(*a)[:max(n, 1)]})
+    mu, sigma, alpha, AEPE, Energy, logP = interp.call(solver, opts, I1, I2, nargout=6)
+    ws = interp.last_workspace
+    out = dict(I1=I1, I2=I2, tflow=tflow, unknown=unk, mu=mu, sigma=sigma, alpha=np.ravel(alpha), AEPE=np.ravel(AEPE),
+               Energy=np.ravel(Energy), logP=np.ravel(logP), pn=np.asarray(ws["pn"]), rou=np.asarray(ws["rou"]), w=np.ravel(ws["w"]),
+               it_end=np.array(int(ws["it"])), T_end=np.array(float(ws["T"])),
+               meta=np.array([Mo, No, L, K, T, drate, lambdas, its, RANGE["minu"], RANGE["maxu"], RANGE["minv"], RANGE["maxv"]]),
+               solver=np.array(solver), probes=np.array(sorted(snaps)))
+    for i, d in enumerate(draws):
+        out["draw%d" % i] = d
+    for it, d in snaps.items():
+        for k, v in d.items():
+            out["p%d_%s" % (it, k)] = np.asarray(v)
+    return out
+
+
+if __name__ == "__main__":
+    for name in (sys.argv[1:] or CASES):
+        t = time.time()
+        out = run_case(name)
+        path = os.path.join(HERE, "refsrc_%s.npz" % name)
+        np.savez_compressed(path, **out)
+        print("%-14s %6.1f s  stopped at it=%d  Energy(1)=%.6e  -> %d KiB" % (name, time.time() - t, int(out["it_end"]), out["Energy"][0],
+                                                                               os.path.getsize(path) // 1024), flush=True)
