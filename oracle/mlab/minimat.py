@@ -426,6 +426,20 @@ class Parser:
                 self.bracket = saved
                 self.paren -= 1
                 e = ("call", e, args)
+            elif tok.kind == "op" and tok.val == "{" and not tok.sp:
+                self.next()
+                self.paren += 1
+                saved, self.bracket = self.bracket, 0
+                args = []
+                while not self.is_op("}"):
+                    if self.is_op(","):
+                        self.next()
+                        continue
+                    args.append(self.parse_expr())
+                self.next()
+                self.bracket = saved
+                self.paren -= 1
+                e = ("cellidx", e, args)
             elif tok.kind == "op" and tok.val == "." and self.peek(1).kind == "id" and not tok.sp:
                 self.next()
                 e = ("field", e, self.next().val)
@@ -499,6 +513,10 @@ def parse_source(src):
 COLON = object()
 
 
+class Cell(list):
+    """1 x n cell array (only what `varargin` needs)"""
+
+
 def norm(v):
     """canonical form of a computed value: 1x1 -> Python scalar, trailing singleton dimensions beyond 2 removed"""
     if isinstance(v, np.ndarray):
@@ -527,6 +545,8 @@ def arr(v):
 
 
 def mshape(v):
+    if isinstance(v, Cell):
+        return (1, len(v)) if len(v) else (0, 0)
     if isinstance(v, np.ndarray):
         return v.shape if v.ndim >= 2 else (1,) + v.shape
     if isinstance(v, str):
@@ -600,7 +620,8 @@ def _fold_shape(shape, n):
 
 def index_get(A, subs):
     if isinstance(A, str):
-        A = np.array([[ord(c) for c in A]], dtype=np.float64)
+        r = index_get(np.array([[float(ord(c)) for c in A]]), subs)
+        return "".join(chr(int(c)) for c in np.ravel(arr(r)))
     A = arr(A)
     n = len(subs)
     if n == 0:
@@ -656,11 +677,33 @@ def index_set(A, subs, value):
             raise MatlabError("growing an array by indexed assignment is not supported")
         flat[idx] = v if is_scalar(v) else flatF(arr(v))
         return flat.reshape(A.shape, order="F")
-    fs = _fold_shape(A.shape, n)
+    empty = A.size == 0
+    fs = _fold_shape(A.shape, n) if not empty else (0,) * n
+    vshape = None if is_scalar(v) else arr(v).shape + (1,) * n
+    if vshape is not None:                                   # value dimensions matched to the non-scalar subscripts, in order
+        vdims = [d for d in vshape if d != 1]
+    need, vi = [], 0
+    for k, sub in enumerate(subs):
+        if sub is COLON:
+            if empty:
+                if vshape is None:
+                    raise MatlabError("A(:,...) = scalar on an undefined array")
+                need.append(vshape[k])
+            else:
+                need.append(fs[k])
+        else:
+            ix = _sub_to_index(sub, fs[k])
+            need.append(max(fs[k], int(ix.max()) + 1 if ix.size else 0))
+    need = tuple(need)
+    if empty or need != tuple(fs):                           # MATLAB grows the array, padding with zeros
+        if not empty and n < A.ndim:
+            raise MatlabError("growing an array through folded trailing dimensions is not supported")
+        dt = A.dtype if not empty else (arr(v).dtype if not is_scalar(v) else np.float64)
+        grown = np.zeros(need, dtype=dt, order="F")
+        if not empty:
+            grown[tuple(slice(0, d) for d in fs)] = A.reshape(fs, order="F")
+        A, fs = grown, need
     idx = [_sub_to_index(s, d) for s, d in zip(subs, fs)]
-    for ix, d in zip(idx, fs):
-        if ix.size and ix.max() >= d:
-            raise MatlabError("growing an array by indexed assignment is not supported")
     out = A.reshape(fs, order="F").copy(order="F")
     tgt = tuple(len(ix) for ix in idx)
     if is_scalar(v):
@@ -853,7 +896,73 @@ def _num2str(a):
     return "%d" % a if a == int(a) else "%.4g" % a
 
 
+def _error(I, n, *a):
+    msg = a[0] if a else "error"
+    try:
+        msg = msg.replace("%d", "%s") % tuple(a[1:]) if len(a) > 1 else msg
+    except (TypeError, ValueError):
+        pass
+    raise MatlabError("error: " + str(msg))
+
+
+def _uint8(a):
+    x = np.asarray(arr(a), dtype=np.float64)
+    r = np.where(x >= 0, np.floor(x + 0.5), -np.floor(-x + 0.5))            # round half away from zero, then saturate
+    return norm(np.asfortranarray(np.clip(np.nan_to_num(r, nan=0.0), 0, 255).astype(np.uint8)))
+
+
+def _strfind(s, pat):
+    hits = [i + 1.0 for i in range(len(s) - len(pat) + 1) if s.startswith(pat, i)] if pat else []
+    return norm(np.array([hits])) if hits else np.zeros((0, 0))
+
+
+_PREC = {"float32": "<f4", "single": "<f4", "int32": "<i4", "uint8": "u1", "double": "<f8", "float64": "<f8"}
+
+
+def _fopen(I, n, name, mode="r"):
+    try:
+        f = open(name, {"r": "rb", "w": "wb"}[mode[0]])
+    except OSError:
+        return (-1.0,)
+    fid = 3.0 + len(I.fids)
+    I.fids[fid] = f
+    return (fid,)
+
+
+def _fread(I, n, fid, count, prec="uint8"):
+    dt = np.dtype(_PREC[prec])
+    k = -1 if math.isinf(float(count)) else int(count)
+    data = np.frombuffer(I.fids[fid].read() if k < 0 else I.fids[fid].read(k * dt.itemsize), dtype=dt).astype(np.float64)
+    return (norm(data.reshape((-1, 1))),) if data.size else (np.zeros((0, 0)),)
+
+
+def _fwrite(I, n, fid, data, prec="uint8"):
+    if isinstance(data, str):
+        I.fids[fid].write(data.encode("latin-1"))
+    else:
+        I.fids[fid].write(flatF(arr(data)).astype(np.dtype(_PREC[prec])).tobytes())
+    return ()
+
+
+def _fclose(I, n, fid):
+    I.fids.pop(fid).close()
+    return ()
+
+
 BUILTINS = {
+    "error": _error,
+    "uint8": lambda I, n, a: (_uint8(a),),
+    "isnan": lambda I, n, a: (math.isnan(a) if is_scalar(a) else norm(np.isnan(arr(a).astype(np.float64))),),
+    "atan2": lambda I, n, y, x: (math.atan2(y, x) if is_scalar(y) and is_scalar(x) else elementwise(np.arctan2, y, x),),
+    "reshape": lambda I, n, a, *d: (norm(np.asfortranarray(arr(a).reshape(_dims(d), order="F"))),),
+    "squeeze": lambda I, n, a: (a if is_scalar(a) or arr(a).ndim <= 2 else
+                                norm(np.asfortranarray(arr(a).reshape([d for d in arr(a).shape if d != 1] or [1], order="F")
+                                                       if sum(d != 1 for d in arr(a).shape) != 1 else
+                                                       arr(a).reshape((-1, 1) if arr(a).shape[0] != 1 or arr(a).shape[1] == 1 else (1, -1),
+                                                                      order="F"))),),
+    "strfind": lambda I, n, s, p: (_strfind(s, p),),
+    "strcmp": lambda I, n, a, b: (bool(isinstance(a, str) and isinstance(b, str) and a == b),),
+    "fopen": _fopen, "fread": _fread, "fwrite": _fwrite, "fclose": _fclose,
     "gpuArray": lambda I, n, a: (a,),
     "gather": lambda I, n, *a: tuple(a[:max(n, 1)]),
     "double": lambda I, n, a: (norm(arr(a).astype(np.float64)),),
@@ -1177,6 +1286,18 @@ class Compiler:
             return mat
         if k == "call":
             return self.call(node, 1, single=True)
+        if k == "cellidx":
+            base, args = self.expr(node[1]), [self.expr(a) for a in node[2]]
+
+            def cidx(fr):
+                c = base(fr)
+                if not isinstance(c, Cell) or len(args) != 1:
+                    raise MatlabError("brace indexing is only supported on 1 x n cell arrays")
+                i = int(args[0](fr))
+                if i < 1 or i > len(c):
+                    raise MatlabError("Index exceeds the number of cell elements")
+                return c[i - 1]
+            return cidx
         raise MatlabError("cannot compile expression node %r" % (k,))
 
     def binop(self, node):
@@ -1317,8 +1438,11 @@ class Compiler:
             get, put = self.var_getter(name), self.var_setter(name)
             argev = self.args(e[2], True)
 
+            isloc = name in self.local
+
             def seti(fr, v):
-                A = get(fr)
+                env = fr.L if isloc else fr.P
+                A = env[name] if name in env else np.zeros((0, 0))       # MATLAB creates the variable
                 put(fr, norm(index_set(A, argev(fr, A), v)))
             return seti
         if e[0] == "field":
@@ -1469,6 +1593,7 @@ class Interp:
         self.on_imwrite = on_imwrite
         self.on_fprintf = on_fprintf
         self.workspaces = []           # workspaces of the active non-nested function calls, innermost last
+        self.fids = {}                 # open files (fopen / fread / fwrite / fclose)
         self.files = {}                # function name -> FuncDef of the file's main function
         self.file_functions = {}       # function name -> all non-nested FuncDefs of that file
         self.last_workspace = None     # local workspace of the most recent top-level call (for state the function does not return)
@@ -1504,9 +1629,13 @@ class Interp:
 
     def call_fdef(self, fd, args, nargout, penv):
         self.calls += 1
-        if len(args) > len(fd.params):
-            raise MatlabError("%s: too many input arguments" % fd.name)
         L = {}
+        if fd.params and fd.params[-1] == "varargin":
+            nfix = len(fd.params) - 1
+            L["varargin"] = Cell(args[nfix:])
+            args = args[:nfix]
+        elif len(args) > len(fd.params):
+            raise MatlabError("%s: too many input arguments" % fd.name)
         for p, a in zip(fd.params, args):
             if p != "~":
                 L[p] = a

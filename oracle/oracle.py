@@ -1,9 +1,8 @@
 """ctypes front-end of the CPU fp64 oracle (oracle/qgmap_oracle.c).  TEST INFRASTRUCTURE ONLY.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
-this module.  find_map and flow_to_color are PINNED against the reference's own .mexw64 binaries (oracle/refbin/);
-PARITY UNPINNED for the rest (see qgmap_oracle.h): the reference's .m files cannot run here and it ships no golden
-vectors; those functions are held in place by closed-form known answers and by the independent NumPy twin.
+this module.  PINNED against the reference, executed (see qgmap_oracle.h): find_map and flow_to_color against the shipped
+.mexw64 binaries (oracle/refbin/), the iteration loop against the reference's own .m files run by oracle/mlab/minimat.py.
 
 All arrays are MATLAB-shaped NumPy fp64 arrays in Fortran (column-major) order, e.g. muu is (M,N,L),
 rou is (M,N,L,2,2) -- exactly the shapes gqmap_gpu_mixture.m:18-24 allocates.

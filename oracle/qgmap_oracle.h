@@ -4,15 +4,15 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library.  The product (libqgmap.so, the CUDA path) never links or calls it.
  *
- * PINNED against the reference's own machine code: qo_find_map (get_map_mex) and qo_flow_to_color
- * (flowToColor_mex) -- oracle/refbin/ runs the shipped .mexw64 binaries natively; outputs bit-identical
- * (tests/test_refbin_get_map.py, tests/test_refbin_flow_to_color.py, vectors under tests/golden/).
- * PARITY UNPINNED for everything else (the iteration loop, profile_logP, AEPE, getVV, GaussHermite_2,
- * projsplx): the reference (motionlife/gqmap-opticalflow) ships those as MATLAB source only, with no
- * tests, golden vectors or saved outputs, and neither MATLAB nor Octave exists in the build container.
- * Those functions are held in place by (i) closed-form known answers derived from the maths
- * (tests/test_oracle_*.py), and (ii) an independently written NumPy twin (oracle/numpy_twin.py) that
- * must agree to fp64 rounding.
+ * PINNED against the reference, executed:
+ *   - qo_find_map (get_map_mex) and qo_flow_to_color (flowToColor_mex) against the shipped .mexw64 binaries, run natively by
+ *     oracle/refbin/ -- bit-identical (tests/test_refbin_get_map.py, tests/test_refbin_flow_to_color.py);
+ *   - the iteration loop (qo_run, qo_gradients, qo_get_vv, qo_gauss_hermite, qo_projsplx, qo_profile_logp, qo_aepe) against the
+ *     reference's own .m files, run unmodified by the mini-MATLAB interpreter oracle/mlab/minimat.py -- fp64 rounding
+ *     (tests/test_refsrc_parity.py, vectors tests/golden/refsrc_*.npz).  The interpreter is ours, MATLAB itself is not
+ *     available: MATLAB's libm, summation order and LAPACK stay unpinned (all at rounding level).
+ * It is additionally held in place by (i) closed-form known answers derived from the maths (tests/test_oracle_*.py), and
+ * (ii) an independently written NumPy twin (oracle/numpy_twin.py) that must agree to fp64 rounding.
  *
  * All arrays are MATLAB column-major fp64: element (m,n,l) of an M x N x L array (1-based) lives at
  * (m-1) + M*(n-1) + M*N*(l-1).  rou is M x N x L x 2 x 2 (edge e: 1=down,2=right; layer c: 1=u,2=v).

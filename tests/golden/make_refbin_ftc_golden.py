@@ -69,7 +69,8 @@ def cases():
     yield "column_vector", np.asfortranarray(rng.normal(0, 1.0, (37, 1, 2)))
     yield "two_rows", np.asfortranarray(rng.normal(0, 1.0, (2, 37, 2)))
     # (a 1 x N field with N > 1 is REJECTED by the binary: MATLAB Coder's run-time check on the vector index `tmp(k0)` of
-    #  computeColor.m:57 raises Coder:FE:PotentialMatrixMatrix; the .m file itself accepts it, and so do the oracle and the product)
+    #  computeColor.m:57 raises Coder:FE:PotentialMatrixMatrix; the .m file fails there too -- the column it gets back no longer
+    #  conforms with the 1 x N arrays around it; the oracle and the product treat 1 x N like any other field)
 
 
 if __name__ == "__main__":

@@ -81,8 +81,35 @@ def run_case(name, its=None, probes=None):
     return out
 
 
+def run_host_io():
+    """The host-side .m files of the drivers' path, executed: readFlowFile.m, legacy/writeFlowFile.m and legacy/flowToColor.m +
+    legacy/computeColor.m with the optional maxFlow argument (the compiled flowToColor_mex takes none)."""
+    import tempfile
+    from oracle.mlab.minimat import Interp
+    interp = Interp([REF, os.path.join(REF, "legacy")])
+    rng = np.random.default_rng(99)
+    flow = np.asfortranarray(rng.normal(0, 2.0, (9, 7, 2)).astype(np.float32).astype(np.float64))       # .flo stores float32
+    flow[2, 3, :] = 1.666666752e9
+    flow[5, 1, 0] = -1.666666752e9
+    out = dict(flow=flow)
+    with tempfile.TemporaryDirectory() as tmp:
+        fn = os.path.join(tmp, "a.flo")
+        interp.call("writeFlowFile", flow, fn, nargout=0)
+        out["flo_bytes"] = np.frombuffer(open(fn, "rb").read(), dtype=np.uint8)
+        out["flo_read_back"] = interp.call("readFlowFile", fn)
+    for tag, mf in (("mf4", 4.0), ("mf05", 0.5), ("mfneg", -1.0)):
+        r = interp.call("flowToColor", flow, mf, nargout=7)
+        out.update({tag + "_img": np.asarray(r[0]), tag + "_flo": np.asarray(r[1]), tag + "_range": np.array([float(x) for x in r[2:6]]),
+                    tag + "_unknown": np.asarray(r[6], dtype=bool), tag + "_maxflow": np.array(mf)})
+    return out
+
+
 if __name__ == "__main__":
-    for name in (sys.argv[1:] or CASES):
+    if not sys.argv[1:] or "host_io" in sys.argv[1:]:
+        out = run_host_io()
+        np.savez_compressed(os.path.join(HERE, "refsrc_host_io.npz"), **out)
+        print("host_io         -> %d KiB" % (os.path.getsize(os.path.join(HERE, "refsrc_host_io.npz")) // 1024), flush=True)
+    for name in ([a for a in sys.argv[1:] if a != "host_io"] or ([] if sys.argv[1:] else CASES)):
         t = time.time()
         out = run_case(name)
         path = os.path.join(HERE, "refsrc_%s.npz" % name)

@@ -167,6 +167,43 @@ def test_reference_source_live(O):
             assert np.array_equal(interp.call(f, V, local="getVV"), O.get_vv(V))
 
 
+# ---- host-side files of the drivers' path: readFlowFile.m, legacy/writeFlowFile.m, legacy/flowToColor.m (+ maxFlow) -----------
+def test_host_io_against_executed_source(pkg, O, tmp_path):
+    d = np.load(os.path.join(GOLD, "refsrc_host_io.npz"))
+    flow = d["flow"]
+    fn = str(tmp_path / "a.flo")
+    pkg.writeFlowFile(flow, fn)                                          # product writer == bytes legacy/writeFlowFile.m produced
+    assert open(fn, "rb").read() == d["flo_bytes"].tobytes()
+    assert np.array_equal(pkg.readFlowFile(fn), d["flo_read_back"]) and np.array_equal(d["flo_read_back"], flow)
+    for tag in ("mf4", "mf05", "mfneg"):                                 # flowToColor(flow, maxFlow): oracle and C ABI, bit for bit
+        mf = float(d[tag + "_maxflow"])
+        for impl in (lambda: O.flow_to_color(flow, mf), lambda: pkg.flowToColor_mex(flow, mf)):
+            r = impl()
+            assert np.array_equal(r[0], d[tag + "_img"]) and np.array_equal(r[1], d[tag + "_flo"]), tag
+            assert tuple(float(x) for x in r[2:6]) == tuple(d[tag + "_range"]) and np.array_equal(np.asarray(r[6], bool), d[tag + "_unknown"])
+    assert not np.array_equal(d["mf4_img"], d["mf05_img"]) and (d["mf05_img"].astype(int).sum() < d["mf4_img"].astype(int).sum())
+
+
+def test_host_io_live(pkg, O, tmp_path):
+    sys.path.insert(0, GOLD)
+    import make_refsrc_golden as G
+    if not os.path.isdir(G.REF):
+        pytest.skip("reference tree not present on this box (the committed vectors cover it)")
+    from oracle.mlab.minimat import Interp
+    from oracle.refbin import refbin
+    interp = Interp([G.REF, os.path.join(G.REF, "legacy")])
+    for seq in ("Venus", "rubberwhale"):
+        fn = os.path.join(G.REF, "middlebury", seq, "flow10.flo")
+        ref = interp.call("readFlowFile", fn)                            # readFlowFile.m executed on a shipped ground-truth file
+        assert np.array_equal(pkg.readFlowFile(fn), ref)
+        out = str(tmp_path / (seq + ".flo"))
+        interp.call("writeFlowFile", ref, out, nargout=0)                # legacy/writeFlowFile.m reproduces the shipped file byte for byte
+        assert open(out, "rb").read() == open(fn, "rb").read()
+        src = interp.call("flowToColor", ref, nargout=7)                 # the .m source == the compiled binary == oracle == product
+        for other in (refbin.flowToColor_mex(ref), O.flow_to_color(ref), pkg.flowToColor_mex(ref)):
+            assert all(np.array_equal(np.asarray(a), np.asarray(b)) for a, b in zip(src, other)), seq
+
+
 # ---- GPU: the CUDA path against the executed source ---------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", SHORT)
