@@ -81,6 +81,56 @@ def run_case(name, its=None, probes=None):
     return out
 
 
+RW_SEED, RW_ITS, RW_STRIDE = 2018, 3, 4
+
+
+def rubberwhale_inputs():
+    """BASELINE configs[0] on the reference's own data: the 96 x 128 crop of the RubberWhale pair committed in rubberwhale_crop.npz
+    (grey frames, ground truth, unknown mask, clamp range of the whole sequence), L=1, K=3, driver constants of optical_flow.m."""
+    z = np.load(os.path.join(HERE, "rubberwhale_crop.npz"))
+    I1, I2 = np.asfortranarray(z["I1"].astype(np.float64)), np.asfortranarray(z["I2"].astype(np.float64))
+    tflow = np.asfortranarray(z["flo"].astype(np.float64))                   # flowToColor_mex's second output (unknowns zeroed)
+    minu, maxu, minv, maxv = (float(x) for x in z["full_stats"])
+    opts = dict(trueFlow=tflow, unknownIdx=np.asfortranarray(z["unknown"]), its=float(RW_ITS), K=3.0, L=1.0, temperature=0.0, drate=0.5,
+                epsn=0.001 ** 2, lambdad=1.0, lambdas=5.0, minu=minu, maxu=maxu, minv=minv, maxv=maxv, dir="/nonexistent")
+    return I1, I2, opts
+
+
+def rubberwhale_draws():
+    rng = np.random.default_rng(RW_SEED)
+    return [rng.random(n).reshape(shp, order="F") for n, shp in ((1, (1, 1)),) + ((96 * 128, (96, 128)),) * 4]
+
+
+def run_rubberwhale():
+    from oracle.mlab.minimat import Interp
+    from oracle.refbin import refbin
+    I1, I2, opts = rubberwhale_inputs()
+    draws = rubberwhale_draws()
+    queue, snaps = list(draws), {}
+
+    def rand(shape):
+        a = queue.pop(0)
+        assert a.size == int(np.prod(shape))
+        return a.reshape(shape, order="F")
+
+    def probe(ws):
+        it = int(ws["it"])
+        d = {f: np.asarray(ws[f], dtype=np.float64) for f in ("muu", "muv", "sigmau", "sigmav", "pn", "rou")}
+        snaps[it] = dict(Energy=float(np.asarray(ws["Energy"]).reshape(-1, order="F")[it - 1]), ptdmu=float(ws["ptdmu"]),
+                         ptdsigma=float(ws["ptdsigma"]), sums=np.array([d[f].sum() for f in d] + [(d[f] ** 2).sum() for f in d]),
+                         **{f: np.array(d[f][::RW_STRIDE, ::RW_STRIDE]) for f in d})
+    interp = Interp([REF], rand=rand, on_fprintf=probe,
+                    externals={"get_map_mex": lambda n, *a: (refbin.get_map_mex(*a),),
+                               "flowToColor_mex": lambda n, *a: refbin.flowToColor_mex(*a)[:max(n, 1)]})
+    mu, sigma, alpha, AEPE, Energy, logP = interp.call("gqmap_gpu_mixture", opts, I1, I2, nargout=6)
+    out = dict(AEPE=np.ravel(AEPE), Energy=np.ravel(Energy), logP=np.ravel(logP), alpha=np.ravel(alpha), seed=np.array(RW_SEED),
+               draws_checksum=np.array([d.sum() for d in draws]))
+    for it, d in snaps.items():
+        for k, v in d.items():
+            out["p%d_%s" % (it, k)] = np.asarray(v)
+    return out
+
+
 def run_host_io():
     """The host-side .m files of the drivers' path, executed: readFlowFile.m, legacy/writeFlowFile.m and legacy/flowToColor.m +
     legacy/computeColor.m with the optional maxFlow argument (the compiled flowToColor_mex takes none)."""
@@ -109,7 +159,13 @@ if __name__ == "__main__":
         out = run_host_io()
         np.savez_compressed(os.path.join(HERE, "refsrc_host_io.npz"), **out)
         print("host_io         -> %d KiB" % (os.path.getsize(os.path.join(HERE, "refsrc_host_io.npz")) // 1024), flush=True)
-    for name in ([a for a in sys.argv[1:] if a != "host_io"] or ([] if sys.argv[1:] else CASES)):
+    if not sys.argv[1:] or "rubberwhale" in sys.argv[1:]:
+        t = time.time()
+        out = run_rubberwhale()
+        np.savez_compressed(os.path.join(HERE, "refsrc_rubberwhale_L1K3.npz"), **out)
+        print("rubberwhale     %6.1f s  Energy=%s AEPE(1)=%.6f -> %d KiB" % (time.time() - t, out["Energy"], out["AEPE"][0],
+                                                                            os.path.getsize(os.path.join(HERE, "refsrc_rubberwhale_L1K3.npz")) // 1024), flush=True)
+    for name in ([a for a in sys.argv[1:] if a not in ("host_io", "rubberwhale")] or ([] if sys.argv[1:] else CASES)):
         t = time.time()
         out = run_case(name)
         path = os.path.join(HERE, "refsrc_%s.npz" % name)

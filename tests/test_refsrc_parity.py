@@ -167,6 +167,67 @@ def test_reference_source_live(O):
             assert np.array_equal(interp.call(f, V, local="getVV"), O.get_vv(V))
 
 
+# ---- BASELINE configs[0] on the reference's own data: RubberWhale crop, L=1, K=3, executed source --------------------------
+def _rubberwhale(O):
+    sys.path.insert(0, GOLD)
+    import make_refsrc_golden as G
+    d = np.load(os.path.join(GOLD, "refsrc_rubberwhale_L1K3.npz"))
+    I1, I2, opts = G.rubberwhale_inputs()
+    draws = G.rubberwhale_draws()
+    assert np.array_equal(np.array([x.sum() for x in draws]), d["draws_checksum"])        # same NumPy stream as when the file was made
+    cfg = O.make_config(96, 128, 1, 3, lambdas=5.0, epsn=opts["epsn"], minu=opts["minu"], maxu=opts["maxu"], minv=opts["minv"], maxv=opts["maxv"])
+    w, ru, rv, su, sv = draws
+    shp = (96, 128, 1)
+    st = O.State(cfg.minu + ru.reshape(shp) * (cfg.maxu - cfg.minu), cfg.minv + rv.reshape(shp) * (cfg.maxv - cfg.minv),
+                 su.reshape(shp) + (cfg.maxu - cfg.minu), sv.reshape(shp) + (cfg.maxv - cfg.minv), np.zeros(shp), np.zeros(shp + (2, 2)), np.ravel(w))
+    return G, d, cfg, I1, I2, opts, st
+
+
+def _rw_check(d, k, st, tol, stride):
+    for f, name in (("muu", "muu"), ("muv", "muv"), ("sigu", "sigmau"), ("sigv", "sigmav"), ("pn", "pn"), ("rou", "rou")):
+        a = getattr(st, f)
+        ref = d["p%d_%s" % (k, name)]
+        _close(a[::stride, ::stride].reshape(ref.shape), ref, tol, (k, f))
+    sums = np.array([getattr(st, f).sum() for f in ("muu", "muv", "sigu", "sigv", "pn", "rou")] +
+                    [(getattr(st, f) ** 2).sum() for f in ("muu", "muv", "sigu", "sigv", "pn", "rou")])
+    assert np.abs(sums - d["p%d_sums" % k]).max() <= tol * 96 * 128 * 40, (k, np.abs(sums - d["p%d_sums" % k]).max())
+
+
+def test_oracle_reproduces_executed_source_on_rubberwhale(O):
+    G, d, cfg, I1, I2, opts, st = _rubberwhale(O)
+    VV = O.get_vv(I2)
+    n, it, stopped, E, dm, ds = O.run(cfg, I1, VV, st.copy(), 1, G.RW_ITS, G.RW_ITS)
+    assert abs(E[0] / d["Energy"][0] - 1) < 1e-13 and np.abs(E / d["Energy"] - 1).max() < 1e-9, np.abs(E / d["Energy"] - 1)
+    one = st.copy()
+    O.run(cfg, I1, VV, one, 1, 10 ** 6, 1)
+    _rw_check(d, 1, one, 1e-10, G.RW_STRIDE)                               # the whole state after the first iteration
+    assert abs(dm[0] / float(d["p1_ptdmu"]) - 1) < 1e-12 and abs(ds[0] / float(d["p1_ptdsigma"]) - 1) < 1e-12
+    mp = np.concatenate([one.muu, one.muv], axis=2)                          # L == 1: map = cat(3, mu_u, mu_v) (:54-55)
+    assert abs(O.aepe(cfg, mp, opts["trueFlow"], opts["unknownIdx"]) / d["AEPE"][0] - 1) < 1e-12
+    assert abs(O.profile_logp(cfg, I1, VV, mp) / d["logP"][0] - 1) < 1e-12
+
+
+@pytest.mark.gpu
+def test_cuda_step_against_executed_source_on_rubberwhale(pkg, O):
+    from test_gpu_parity import _round_state
+    G, d, cfg, I1, I2, opts, st = _rubberwhale(O)
+    before = _round_state(st)
+    with pkg.Solver(options_from_cfg(cfg), I1, I2) as s:
+        s.set_state(state_dict(before), it=1, alpha=before.alpha)
+        r = s.step(1)
+        got = s.get_state()
+        mp = s.map()
+        lp, ae = s.logp(mp), s.aepe(mp, opts["trueFlow"], opts["unknownIdx"])
+    assert abs(r["Energy"][0] / d["Energy"][0] - 1) < 1e-5, (r["Energy"][0], d["Energy"][0])       # north_star: 1e-4
+    assert abs(r["ptdmu"][0] / float(d["p1_ptdmu"]) - 1) < 1e-4 and abs(r["ptdsigma"][0] / float(d["p1_ptdsigma"]) - 1) < 1e-4
+    assert abs(ae / d["AEPE"][0] - 1) < 1e-5 and abs(lp / d["logP"][0] - 1) < 1e-5
+    sgot = dict(muu=got["muu"], muv=got["muv"], sigmau=got["sigmau"], sigmav=got["sigmav"])
+    for f in sgot:                                                          # first step from sigma ~ 7: gradients O(1..30), fp32 evaluation
+        ref = d["p1_%s" % f]
+        err = np.abs(sgot[f][::G.RW_STRIDE, ::G.RW_STRIDE].reshape(ref.shape) - ref)
+        assert err.max() < 2e-4 and np.median(err) < 2e-6, (f, float(err.max()), float(np.median(err)))
+
+
 # ---- host-side files of the drivers' path: readFlowFile.m, legacy/writeFlowFile.m, legacy/flowToColor.m (+ maxFlow) -----------
 def test_host_io_against_executed_source(pkg, O, tmp_path):
     d = np.load(os.path.join(GOLD, "refsrc_host_io.npz"))
