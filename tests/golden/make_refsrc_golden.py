@@ -23,8 +23,12 @@ CASES = {
     "full_alpha":     ("gqmap_gpu_mixture", 5, 5, 2, 3, 0.0, 0.5, 5.0, 504, (1, 499, 500, 501, 502, 503, 504), 14),
     "super_L2K3_T":   ("gqmap_gpuSuper_mix_entropy", 16, 20, 2, 3, 0.2, 0.75, 16.0, 3, (1, 2, 3), 15),
     "super_anneal":   ("gqmap_gpuSuper_mix_entropy", 12, 12, 2, 2, 0.2, 0.75, 16.0, 502, (1, 498, 499, 500, 501, 502), 16),
+    "super_L1K3":     ("gqmap_gpuSuper_mix_entropy", 16, 16, 1, 3, 0.2, 0.75, 16.0, 2, (1, 2), 17),
+    "full_zero_v":    ("gqmap_gpu_mixture", 8, 8, 2, 3, 0.0, 0.5, 5.0, 3, (1, 2, 3), 18),      # Venus/Teddy/Cones: minv = maxv = 0
+    "full_L2K5":      ("gqmap_gpu_mixture", 7, 7, 2, 5, 0.1, 0.5, 5.0, 2, (1, 2), 19),
 }
 RANGE = dict(minu=-3.0, maxu=2.0, minv=-1.5, maxv=4.0)
+CASE_RANGE = {"full_zero_v": dict(minu=-9.375, maxu=7.0, minv=0.0, maxv=0.0)}                    # the Venus ground-truth range
 PROBE_FIELDS = ("muu", "muv", "sigmau", "sigmav", "pn", "rou", "w", "alpha")
 
 
@@ -46,8 +50,9 @@ def run_case(name, its=None, probes=None):
     its = its0 if its is None else its
     probes = probes0 if probes is None else probes
     I1, I2, tflow, unk = frames(Mo, No, seed)
+    rg = CASE_RANGE.get(name, RANGE)
     opts = dict(trueFlow=tflow, unknownIdx=unk, its=float(its), K=float(K), L=float(L), temperature=T, drate=drate, epsn=1e-6,
-                lambdad=1.0, lambdas=lambdas, dir="/nonexistent", **RANGE)
+                lambdad=1.0, lambdas=lambdas, dir="/nonexistent", **rg)
     rng = np.random.default_rng(seed + 1000)
     draws, snaps = [], {}
 
@@ -71,7 +76,7 @@ def run_case(name, its=None, probes=None):
     out = dict(I1=I1, I2=I2, tflow=tflow, unknown=unk, mu=mu, sigma=sigma, alpha=np.ravel(alpha), AEPE=np.ravel(AEPE),
                Energy=np.ravel(Energy), logP=np.ravel(logP), pn=np.asarray(ws["pn"]), rou=np.asarray(ws["rou"]), w=np.ravel(ws["w"]),
                it_end=np.array(int(ws["it"])), T_end=np.array(float(ws["T"])),
-               meta=np.array([Mo, No, L, K, T, drate, lambdas, its, RANGE["minu"], RANGE["maxu"], RANGE["minv"], RANGE["maxv"]]),
+               meta=np.array([Mo, No, L, K, T, drate, lambdas, its, rg["minu"], rg["maxu"], rg["minv"], rg["maxv"]]),
                solver=np.array(solver), probes=np.array(sorted(snaps)))
     for i, d in enumerate(draws):
         out["draw%d" % i] = d

@@ -21,7 +21,7 @@ from conftest import options_from_cfg, state_dict
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = os.path.join(HERE, "golden")
-SHORT = ("full_L2K3", "full_L1K4", "full_L3K3_T", "super_L2K3_T")
+SHORT = ("full_L2K3", "full_L1K4", "full_L3K3_T", "super_L2K3_T", "super_L1K3", "full_zero_v", "full_L2K5")
 LONG = ("full_alpha", "super_anneal")
 
 
@@ -133,7 +133,7 @@ def test_oracle_single_steps_from_probed_states(O, name):
         if k + 2 in probes:                                             # T in effect for the following iteration (anneal at it % 500 == 0)
             assert st.T == float(d["p%d_T" % (k + 2)]), (k, st.T)
         done += 1
-    assert done >= 2
+    assert done >= 1
     if name == "super_anneal":
         assert float(d["p500_T"]) == 0.2 and abs(float(d["p501_T"]) - 0.15) < 1e-16
     if name == "full_alpha":
