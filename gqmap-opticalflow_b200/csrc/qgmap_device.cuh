@@ -246,14 +246,29 @@ struct QgTapCache {
 
 // sqrt(eps + (I1 - bicubic(VV))^2) at displacement x = (x1 horizontal, x2 vertical) from pixel (m,n) (0-based).
 // node_pot = -lambdad * this  (gqmap_gpu_mixture.m:156-179).  x- and y-axis arithmetic runs as one fp32x2 stream.
+// CLAMP_FIRST: the reference clamping (:157-162: Xq = min(max(j + x1, 1), N), cell index capped at N-1) is applied to the
+// displacement itself, in coordinates relative to the pixel, where the bounds are small integers and exact in fp32: four FMNMX
+// instead of the twelve compare/select instructions of clamping cell index and fraction separately.  A sample clamped at the far
+// edge lands on cell last+1 with fraction 0 instead of cell last with fraction 1 -- the same tap with weight exactly 2, the other
+// weights exactly 0, and the gather layout is zero-filled beyond the padded image: the value is bit-identical (the Energy of a
+// 4000-iteration run does not change in any digit).  Measured (profiles/r01_tile_ab.txt, experiment 9): +3..4% for K >= 7
+// (issue-bound, 72 registers); -1..-3% for K <= 5 and -7% for the super-pixel kernel, whose register budgets (64 / 96) turn the
+// four extra live bounds into spills -- so it is a per-instantiation choice.
+template <bool CLAMP_FIRST>
 __device__ __forceinline__ float qg_node_sample(const QgTap8 *__restrict__ VV8, int pitchV, int m, int n, int lastx,
                                                 int lasty, float2 x, float I1v, float epsn, QgTapCache &tc)
 {
     int ix, iy;
+    if (CLAMP_FIRST) {
+        x.x = fminf(fmaxf(x.x, (float)(-n)), (float)(lastx + 1 - n));
+        x.y = fminf(fmaxf(x.y, (float)(-m)), (float)(lasty + 1 - m));
+    }
     float2 fr = qg_floor_split2(x, ix, iy);
     ix += n; iy += m;
-    if (ix < 0) { ix = 0; fr.x = 0.0f; } else if (ix > lastx) { ix = lastx; fr.x = 1.0f; }     // reference clamping :157-162
-    if (iy < 0) { iy = 0; fr.y = 0.0f; } else if (iy > lasty) { iy = lasty; fr.y = 1.0f; }
+    if (!CLAMP_FIRST) {
+        if (ix < 0) { ix = 0; fr.x = 0.0f; } else if (ix > lastx) { ix = lastx; fr.x = 1.0f; }     // reference clamping :157-162
+        if (iy < 0) { iy = 0; fr.y = 0.0f; } else if (iy > lasty) { iy = lasty; fr.y = 1.0f; }
+    }
     if (ix != tc.ix || iy != tc.iy) {
         const QgTap8 *r0 = VV8 + (long long)iy * pitchV + ix;    // padded coords: taps rows iy..iy+3, cols ix..ix+3
         tc.v01 = qg_ld256(r0);
@@ -325,7 +340,7 @@ __device__ __forceinline__ float qg_super_sample(const QgTap8 *__restrict__ VV8,
 #pragma unroll 1
             for (int dj = 0; dj < 4; ++dj) {
                 QgTapCache tc;
-                acc += qg_node_sample(VV8, pitchV, m4 + di, n4 + dj, lastx, lasty, x, I1b[di * 4 + dj], epsn, tc);
+                acc += qg_node_sample<false>(VV8, pitchV, m4 + di, n4 + dj, lastx, lasty, x, I1b[di * 4 + dj], epsn, tc);
             }
     }
     return acc;

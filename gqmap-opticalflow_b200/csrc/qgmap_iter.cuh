@@ -211,7 +211,7 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
             const int lastx = p.No - 2, lasty = p.Mo - 2;
             QgTapCache tc;
             mo = qg_quadrature<KT>(p.tab, p.K, muu, muv, sigu, sigv, sp, -p.lambdad, [&](float2 x) {
-                return qg_node_sample(p.VV8, p.pitchV, m, n, lastx, lasty, x, I1v, p.epsn, tc);
+                return qg_node_sample<(KT >= 7)>(p.VV8, p.pitchV, m, n, lastx, lasty, x, I1v, p.epsn, tc);
             });
         }
         const QgGrad gn = qg_epilogue(mo, sp, a, sigu, sigv, pn, -3.0f * T);
@@ -342,7 +342,7 @@ qgmap_iter_kernel_g4(const __grid_constant__ QgIterParams p)
             const int lastx = p.No - 2, lasty = p.Mo - 2;
             QgTapCache tc;
             mo = qg_quadrature<KT>(p.tab, p.K, muu, muv, sigu, sigv, sp, -p.lambdad, [&](float2 x) {
-                return qg_node_sample(p.VV8, p.pitchV, m, n, lastx, lasty, x, I1v, p.epsn, tc);
+                return qg_node_sample<(KT >= 7)>(p.VV8, p.pitchV, m, n, lastx, lasty, x, I1v, p.epsn, tc);
             }, g, QG_G);
         }
     }
