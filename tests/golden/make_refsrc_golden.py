@@ -26,6 +26,9 @@ CASES = {
     "super_L1K3":     ("gqmap_gpuSuper_mix_entropy", 16, 16, 1, 3, 0.2, 0.75, 16.0, 2, (1, 2), 17),
     "full_zero_v":    ("gqmap_gpu_mixture", 8, 8, 2, 3, 0.0, 0.5, 5.0, 3, (1, 2, 3), 18),      # Venus/Teddy/Cones: minv = maxv = 0
     "full_L2K5":      ("gqmap_gpu_mixture", 7, 7, 2, 5, 0.1, 0.5, 5.0, 2, (1, 2), 19),
+    # K >= 7 runs the clamp-first sample path of the CUDA kernel; on images this small most quadrature points are clamped to the border
+    "full_L2K9":      ("gqmap_gpu_mixture", 6, 7, 2, 9, 0.0, 0.5, 5.0, 2, (1, 2), 20),
+    "full_L1K7":      ("gqmap_gpu_mixture", 9, 6, 1, 7, 0.2, 0.5, 5.0, 2, (1, 2), 21),
 }
 RANGE = dict(minu=-3.0, maxu=2.0, minv=-1.5, maxv=4.0)
 CASE_RANGE = {"full_zero_v": dict(minu=-9.375, maxu=7.0, minv=0.0, maxv=0.0)}                    # the Venus ground-truth range

@@ -21,7 +21,7 @@ from conftest import options_from_cfg, state_dict
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = os.path.join(HERE, "golden")
-SHORT = ("full_L2K3", "full_L1K4", "full_L3K3_T", "super_L2K3_T", "super_L1K3", "full_zero_v", "full_L2K5")
+SHORT = ("full_L2K3", "full_L1K4", "full_L3K3_T", "super_L2K3_T", "super_L1K3", "full_zero_v", "full_L2K5", "full_L2K9", "full_L1K7")
 LONG = ("full_alpha", "super_anneal")
 
 
