@@ -23,8 +23,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = os.path.join(HERE, "golden")
 SHORT = ("full_L2K3", "full_L1K4", "full_L3K3_T", "super_L2K3_T", "super_L1K3", "full_zero_v", "full_L2K5", "full_L2K9", "full_L1K7")
 LONG = ("full_alpha", "super_anneal")
-# the cases whose CUDA comparison has been run on a B200; QGMAP_REFSRC_ALL=1 adds the K=7/9 files (checked on CPU until then)
-GPU_CASES = SHORT if os.environ.get("QGMAP_REFSRC_ALL") else SHORT[:7]
+GPU_CASES = SHORT
 
 
 def load(name):
