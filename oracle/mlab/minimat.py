@@ -24,7 +24,7 @@ import numpy as np
 
 
 class MatlabError(RuntimeError):
-    pass
+    ident = ""
 
 
 # ======================================================================================================================
@@ -469,6 +469,20 @@ class Parser:
                 self.paren -= 1
                 return ("paren", e)
             if tok.val == "@":
+                if self.is_op("("):                                  # anonymous function  @(a,b) expr
+                    self.next()
+                    params = []
+                    while not self.is_op(")"):
+                        if self.is_op(","):
+                            self.next()
+                            continue
+                        params.append(self.next().val)
+                    self.next()
+                    saved_b, saved_p = self.bracket, self.paren
+                    self.bracket, self.paren = 0, 0
+                    body = self.parse_expr()
+                    self.bracket, self.paren = saved_b, saved_p
+                    return ("anon", params, body)
                 return ("handle", self.next().val)
             if tok.val == "[":
                 return self.parse_matrix()
@@ -897,12 +911,23 @@ def _num2str(a):
 
 
 def _error(I, n, *a):
+    ident = ""
+    if len(a) >= 2 and isinstance(a[0], str) and ":" in a[0] and " " not in a[0]:       # error(id, msg, ...)
+        ident, a = a[0], a[1:]
     msg = a[0] if a else "error"
     try:
         msg = msg.replace("%d", "%s") % tuple(a[1:]) if len(a) > 1 else msg
     except (TypeError, ValueError):
         pass
-    raise MatlabError("error: " + str(msg))
+    e = MatlabError("error: " + str(msg))
+    e.ident = ident
+    raise e
+
+
+def _struct(*a):
+    if len(a) % 2:
+        raise MatlabError("struct: field names and values must come in pairs")
+    return {str(a[i]): a[i + 1] for i in range(0, len(a), 2)}
 
 
 def _uint8(a):
@@ -950,6 +975,12 @@ def _fclose(I, n, fid):
 
 
 BUILTINS = {
+    "isfield": lambda I, n, s, f: (bool(isinstance(s, dict) and f in s),),
+    "struct": lambda I, n, *a: (_struct(*a),),
+    "ceil": _un(lambda x: float(math.ceil(x)) if math.isfinite(x) else x, np.ceil),
+    "round": _un(lambda x: float(math.floor(abs(x) + 0.5)) * (1.0 if x >= 0 else -1.0) if math.isfinite(x) else x,
+                 lambda v: np.where(v >= 0, np.floor(v + 0.5), -np.floor(-v + 0.5))),
+    "onCleanup": lambda I, n, f: (Cleanup(f),),
     "error": _error,
     "uint8": lambda I, n, a: (_uint8(a),),
     "isnan": lambda I, n, a: (math.isnan(a) if is_scalar(a) else norm(np.isnan(arr(a).astype(np.float64))),),
@@ -1023,6 +1054,18 @@ class Frame:
 class FuncHandle:
     def __init__(self, fdef, penv):
         self.fdef, self.penv = fdef, penv
+
+
+class AnonFunc:
+    """@(params) expr -- the workspace is captured BY VALUE when the handle is created, as in MATLAB"""
+    def __init__(self, params, body, captured, body0=None):
+        self.params, self.body, self.captured, self.body0 = params, body, captured, body0
+
+
+class Cleanup:
+    """onCleanup(f): f runs when the function that holds the object returns (normally or through an error)"""
+    def __init__(self, fn):
+        self.fn = fn
 
 
 class _Break(Exception):
@@ -1286,6 +1329,17 @@ class Compiler:
             return mat
         if k == "call":
             return self.call(node, 1, single=True)
+        if k == "anon":
+            params, body_node = node[1], node[2]
+            sub = Compiler.__new__(Compiler)
+            sub.I, sub.f, sub.file_funcs = self.I, self.f, self.file_funcs
+            sub.local = set(params) | self.local | self.shared            # everything resolves in the captured snapshot
+            sub.shared = set()
+            sub.siblings, sub.children = self.siblings, self.children
+            sub._anon_parent = self
+            body = sub.expr(body_node)
+            body0 = sub.call(body_node, 0, single=False) if body_node[0] == "call" else None     # called as a statement: no output needed
+            return lambda fr: AnonFunc(params, body, {**(fr.P or {}), **fr.L}, body0)
         if k == "cellidx":
             base, args = self.expr(node[1]), [self.expr(a) for a in node[2]]
 
@@ -1409,7 +1463,7 @@ class Compiler:
                     if k == s and 1 <= k <= A.size:
                         r = A.reshape(-1, order="F")[k - 1].item()
                         return r if single else (r,)
-                if isinstance(A, FuncHandle):
+                if isinstance(A, (FuncHandle, AnonFunc)):
                     r = self.I.call_handle(A, [s], nargout)
                     return r[0] if single else r
                 r = index_get(A, [s])
@@ -1418,9 +1472,9 @@ class Compiler:
 
         def idx(fr):
             A = getbase(fr)
-            if isinstance(A, FuncHandle):
+            if isinstance(A, (FuncHandle, AnonFunc)):
                 r = self.I.call_handle(A, argev(fr, None), nargout)
-                return r[0] if single else r
+                return (r[0] if r else None) if single else r
             r = index_get(A, argev(fr, A))
             return r if single else (r,)
         return idx
@@ -1480,7 +1534,9 @@ class Compiler:
                     put(fr, val(fr))
                 except MatlabError as e:
                     if "line " not in str(e)[:40]:
-                        raise MatlabError("%s line %d: %s" % (self.f.name, line, e))
+                        wrapped = MatlabError("%s line %d: %s" % (self.f.name, line, e))
+                        wrapped.ident = e.ident
+                        raise wrapped
                     raise
             return do
         if k == "massign":
@@ -1649,6 +1705,9 @@ class Interp:
         finally:
             if penv is None:
                 self.workspaces.pop()
+            for v in reversed(list(L.values())):
+                if isinstance(v, Cleanup):
+                    self.call_handle(v.fn, [], 0)
         k = max(nargout, 1) if fd.outs else 0
         if nargout > len(fd.outs):
             raise MatlabError("%s: too many output arguments" % fd.name)
@@ -1664,6 +1723,16 @@ class Interp:
         return tuple(out)
 
     def call_handle(self, fh, args, nargout):
+        if isinstance(fh, AnonFunc):
+            if len(args) > len(fh.params):
+                raise MatlabError("too many input arguments to an anonymous function")
+            L = dict(fh.captured)
+            L.update(zip(fh.params, args))
+            if nargout == 0 and fh.body0 is not None:
+                r = fh.body0(Frame(L, None, 0))
+                return tuple(r) if isinstance(r, (tuple, list)) else ((r,) if r is not None else ())
+            r = fh.body(Frame(L, None, nargout))
+            return r if isinstance(r, tuple) else (r,)
         return self.call_fdef(fh.fdef, args, nargout, fh.penv)
 
     def call(self, name, *args, nargout=1, local=None):
