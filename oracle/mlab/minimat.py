@@ -178,9 +178,12 @@ class Parser:
     def parse_file(self):
         funcs = []
         self.skip_seps()
+        if self.peek().kind != "eof" and not self.is_kw("function"):          # a script: one body, its workspace is the result
+            body = self.parse_block(())
+            return [FuncDef("<script>", [], [], body, [], 1)]
         while self.peek().kind != "eof":
             if not self.is_kw("function"):
-                raise MatlabError("line %d: scripts are not supported (expected `function`)" % self.peek().line)
+                raise MatlabError("line %d: expected `function`" % self.peek().line)
             funcs.append(self.parse_function())
             self.skip_seps()
         return funcs
@@ -486,15 +489,20 @@ class Parser:
                 return ("handle", self.next().val)
             if tok.val == "[":
                 return self.parse_matrix()
+            if tok.val == "{":
+                m = self.parse_matrix(closer="}")
+                if len(m[1]) > 1:
+                    raise MatlabError("line %d: only 1 x n cell literals are supported" % tok.line)
+                return ("cell", m[1][0] if m[1] else [])
         raise MatlabError("line %d: unexpected token %r" % (tok.line, tok.val))
 
-    def parse_matrix(self):
+    def parse_matrix(self, closer="]"):
         rows, row = [], []
         saved_b, saved_p = self.bracket, self.paren
         self.bracket, self.paren = 1, 0
         while True:
             tok = self.peek()
-            if tok.kind == "op" and tok.val == "]":
+            if tok.kind == "op" and tok.val == closer:
                 self.next()
                 break
             if tok.kind == "op" and tok.val == ",":
@@ -975,6 +983,8 @@ def _fclose(I, n, fid):
 
 
 BUILTINS = {
+    "clear": lambda I, n, *a: (),
+    "save": lambda I, n, fn, *names: (I.on_save(fn, names, I.workspaces[-1]) if I.on_save else None, ())[1],
     "isfield": lambda I, n, s, f: (bool(isinstance(s, dict) and f in s),),
     "struct": lambda I, n, *a: (_struct(*a),),
     "ceil": _un(lambda x: float(math.ceil(x)) if math.isfinite(x) else x, np.ceil),
@@ -1329,6 +1339,9 @@ class Compiler:
             return mat
         if k == "call":
             return self.call(node, 1, single=True)
+        if k == "cell":
+            elems = [self.expr(e) for e in node[1]]
+            return lambda fr: Cell(e(fr) for e in elems)
         if k == "anon":
             params, body_node = node[1], node[2]
             sub = Compiler.__new__(Compiler)
@@ -1648,6 +1661,7 @@ class Interp:
         self.rand = rand or (lambda shape: self._rng.random(int(np.prod(shape))).reshape(shape, order="F"))
         self.on_imwrite = on_imwrite
         self.on_fprintf = on_fprintf
+        self.on_save = None            # f(filename, variable names, workspace) for `save(filename, 'a', 'b', ...)`
         self.workspaces = []           # workspaces of the active non-nested function calls, innermost last
         self.fids = {}                 # open files (fopen / fread / fwrite / fclose)
         self.files = {}                # function name -> FuncDef of the file's main function
@@ -1734,6 +1748,18 @@ class Interp:
             r = fh.body(Frame(L, None, nargout))
             return r if isinstance(r, tuple) else (r,)
         return self.call_fdef(fh.fdef, args, nargout, fh.penv)
+
+    def run_script(self, path):
+        """Execute a script file; returns its workspace (dict)."""
+        with open(path, "r", encoding="latin-1") as f:
+            funcs = parse_source(f.read())
+        if len(funcs) != 1 or funcs[0].name != "<script>":
+            raise MatlabError("%s is not a script" % path)
+        fd = funcs[0]
+        fd.parent = None
+        self._compile(fd, {})
+        self.call_fdef(fd, [], 0, None)
+        return self.last_workspace
 
     def call(self, name, *args, nargout=1, local=None):
         """Call the main function of <name>.m found on the search path (or, with local=, another non-nested function of that

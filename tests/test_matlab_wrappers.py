@@ -225,3 +225,67 @@ def test_wrappers_through_the_real_gateway(pkg, variant, tmp_path):
     for g, w in zip(chunked, ref):
         assert np.array_equal(np.asarray(g).reshape(w.shape), w, equal_nan=True)
     assert [os.path.basename(p) for p in pngs] == ["1.png", "3.png", "6.png"]
+
+
+# ---- the reference's own DRIVER SCRIPTS, unmodified, on top of the wrappers -------------------------------------------------------
+REF = "/root/reference"
+
+
+def _driver_interp(pkg, solve):
+    """Search path = our wrappers first, then the reference tree: optical_flow.m finds OUR gqmap_gpu_mixture.m and the reference's
+    readFlowFile.m; flowToColor_mex is the real Linux MEX gateway; toolbox functions (imread, rgb2gray, imresize) are supplied here."""
+    from PIL import Image
+    ext = _real_gateway(pkg)
+    ext["gqmap_mex"] = solve
+
+    def imread(nargout, path):
+        return (np.asfortranarray(np.asarray(Image.open(os.path.join(REF, path)).convert("RGB"))),)
+
+    def imresize(nargout, img, scale):
+        assert scale == 1.0                                              # both drivers use scale = 1
+        return (img,)
+    ext.update(imread=imread, imresize=imresize, rgb2gray=lambda n, rgb: (np.asfortranarray(pkg.rgb2gray(np.asarray(rgb))),))
+    I = Interp([MDIR, REF], externals=ext)
+    saved = []
+    I.on_save = lambda fn, names, ws: saved.append((fn, names, {k: ws[k] for k in names}))
+    return I, saved
+
+
+@pytest.mark.parametrize("script,solver,variant,seqs,K,lambdas,T", [
+    ("optical_flow.m", "gqmap_gpu_mixture", 0.0, ["Teddy", "Cones"], 9.0, 5.0, 0.0),
+    ("optical_flowSuper.m", "gqmap_gpuSuper_mix_entropy", 1.0, ["Venus", "Hydrangea", "Urban2", "Urban3", "Grove3"], 11.0, 16.0, 0.2)])
+def test_reference_driver_scripts_run_unmodified_on_the_wrappers(pkg, script, solver, variant, seqs, K, lambdas, T):
+    """The drop-in claim, executed: the reference's experiment drivers run as they are; only the functions behind the names changed."""
+    if not os.path.isdir(REF):
+        pytest.skip("reference tree not present on this box")
+    calls = []
+
+    def solve(nargout, cmd, *a):                                         # stands in for the GPU: record the request, return shaped outputs
+        assert cmd == "solve" and nargout == 6
+        calls.append(a)
+        o, I1 = a[1], np.asarray(a[2])
+        its, L = int(o["its"]), int(o["L"])
+        b = 4 if a[0] == 1.0 else 1
+        shp = (I1.shape[0] // b, I1.shape[1] // b, L, 2)
+        return (np.zeros(shp, order="F"), np.ones(shp, order="F"), np.full((1, 1, L), 1.0 / L), np.full((its, 1), np.nan), np.zeros((its, 1)),
+                np.full((its, 1), np.nan))
+    I, saved = _driver_interp(pkg, solve)
+    cwd = os.getcwd()
+    try:
+        os.chdir(REF)                                                    # the scripts use paths relative to the reference root
+        ws = I.run_script(os.path.join(REF, script))
+    finally:
+        os.chdir(cwd)
+    assert len(calls) == len(seqs) == len(saved)
+    for (var, o, I1, I2), seq, (fn, names, vals) in zip(calls, seqs, saved):
+        assert var == variant and (o["K"], o["L"], o["its"], o["lambdas"], o["lambdad"], o["temperature"], o["epsn"]) == (K, 3.0, 30000.0, lambdas, 1.0, T, 1e-6)
+        d = seq if seq != "RubberWhale" else "rubberwhale"
+        flow = pkg.readFlowFile(os.path.join(REF, "middlebury", d, "flow10.flo"))
+        img, flo, minu, maxu, minv, maxv, unk = pkg.flowToColor_mex(flow)                    # what optical_flow.m:12-13 must have produced
+        assert np.array_equal(o["trueFlow"], flo) and np.array_equal(np.asarray(o["unknownIdx"], bool), unk)
+        assert (o["minu"], o["maxu"], o["minv"], o["maxv"]) == (minu, maxu, minv, maxv)
+        assert np.asarray(I1).shape == flow.shape[:2] and np.asarray(I1).dtype == np.float64 and 0 <= np.asarray(I1).min() and np.asarray(I1).max() <= 255
+        assert not np.array_equal(I1, I2)
+        assert fn.endswith("/" + seq + ".mat") and set(names) == {"options", "AEPE", "mu", "sigma", "alpha", "Energy", "logP"}     # optical_flow.m:28
+        assert vals["options"]["dir"] == fn[:-len("/" + seq + ".mat")]
+    assert ws["name"] == seqs[-1]
