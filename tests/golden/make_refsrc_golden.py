@@ -139,6 +139,51 @@ def run_rubberwhale():
     return out
 
 
+def run_rubberwhale_full():
+    """BASELINE configs[0] at FULL size: the whole 388 x 584 RubberWhale pair (MATLAB rgb2gray of the shipped PNGs), L=1, K=3, one
+    iteration of gqmap_gpu_mixture.m incl. its monitoring -- about ten minutes under the interpreter.  The grey frames are stored
+    (uint8) so that the GPU box can repeat the step; the ground truth is used for AEPE(1) here but not stored."""
+    from PIL import Image
+    from oracle.mlab.minimat import Interp
+    from oracle.refbin import refbin
+    d = os.path.join(REF, "middlebury", "rubberwhale")
+
+    def grey(fn):                                                            # MATLAB rgb2gray on uint8: weighted sum, rounded
+        rgb = np.asarray(Image.open(os.path.join(d, fn)).convert("RGB")).astype(np.float64)
+        return np.floor(rgb[..., 0] * 0.298936021293775 + rgb[..., 1] * 0.587043074451121 + rgb[..., 2] * 0.114020904255103 + 0.5).astype(np.uint8)
+    g1, g2 = grey("frame10.png"), grey("frame11.png")
+    z = np.load(os.path.join(HERE, "rubberwhale_crop.npz"))
+    assert [int(g1.astype(np.int64).sum()), int(g2.astype(np.int64).sum())] == list(z["grey_checksum"])       # same conversion as the crop fixture
+    Mo, No = g1.shape
+    with open(os.path.join(d, "flow10.flo"), "rb") as f:
+        f.read(12)
+        gt = np.fromfile(f, np.float32).reshape(Mo, No, 2).astype(np.float64)
+    _, tflow, minu, maxu, minv, maxv, unk = refbin.flowToColor_mex(np.asfortranarray(gt))                      # optical_flow.m:12-13, the binary
+    I1, I2 = np.asfortranarray(g1.astype(np.float64)), np.asfortranarray(g2.astype(np.float64))
+    opts = dict(trueFlow=tflow, unknownIdx=unk, its=1.0, K=3.0, L=1.0, temperature=0.0, drate=0.5, epsn=0.001 ** 2, lambdad=1.0,
+                lambdas=5.0, minu=minu, maxu=maxu, minv=minv, maxv=maxv, dir="/nonexistent")
+    rng = np.random.default_rng(RW_SEED + 1)
+    draws = [rng.random(n).reshape(shp, order="F") for n, shp in ((1, (1, 1)),) + ((Mo * No, (Mo, No)),) * 4]
+    queue, snap = list(draws), {}
+
+    def rand(shape):
+        return queue.pop(0).reshape(shape, order="F")
+
+    def probe(ws):
+        dd = {f: np.asarray(ws[f], dtype=np.float64) for f in ("muu", "muv", "sigmau", "sigmav", "pn", "rou")}
+        snap.update(ptdmu=float(ws["ptdmu"]), ptdsigma=float(ws["ptdsigma"]),
+                    sums=np.array([dd[f].sum() for f in dd] + [(dd[f] ** 2).sum() for f in dd]),
+                    **{f: np.array(dd[f][::8, ::8]) for f in dd})
+    interp = Interp([REF], rand=rand, on_fprintf=probe,
+                    externals={"get_map_mex": lambda n, *a: (refbin.get_map_mex(*a),),
+                               "flowToColor_mex": lambda n, *a: refbin.flowToColor_mex(*a)[:max(n, 1)]})
+    mu, sigma, alpha, AEPE, Energy, logP = interp.call("gqmap_gpu_mixture", opts, I1, I2, nargout=6)
+    out = dict(I1=g1, I2=g2, range=np.array([minu, maxu, minv, maxv]), AEPE=np.ravel(AEPE), Energy=np.ravel(Energy), logP=np.ravel(logP),
+               seed=np.array(RW_SEED + 1), draws_checksum=np.array([x.sum() for x in draws]))
+    out.update({"p1_" + k: np.asarray(v) for k, v in snap.items()})
+    return out
+
+
 def run_host_io():
     """The host-side .m files of the drivers' path, executed: readFlowFile.m, legacy/writeFlowFile.m and legacy/flowToColor.m +
     legacy/computeColor.m with the optional maxFlow argument (the compiled flowToColor_mex takes none)."""
@@ -173,7 +218,14 @@ if __name__ == "__main__":
         np.savez_compressed(os.path.join(HERE, "refsrc_rubberwhale_L1K3.npz"), **out)
         print("rubberwhale     %6.1f s  Energy=%s AEPE(1)=%.6f -> %d KiB" % (time.time() - t, out["Energy"], out["AEPE"][0],
                                                                             os.path.getsize(os.path.join(HERE, "refsrc_rubberwhale_L1K3.npz")) // 1024), flush=True)
-    for name in ([a for a in sys.argv[1:] if a not in ("host_io", "rubberwhale")] or ([] if sys.argv[1:] else CASES)):
+    if "rubberwhale_full" in sys.argv[1:]:                                  # ~10 minutes: only on request
+        t = time.time()
+        out = run_rubberwhale_full()
+        np.savez_compressed(os.path.join(HERE, "refsrc_rubberwhale_full_L1K3.npz"), **out)
+        print("rubberwhale_full %6.1f s  Energy(1)=%.9e AEPE(1)=%.6f logP(1)=%.6e -> %d KiB" % (
+            time.time() - t, out["Energy"][0], out["AEPE"][0], out["logP"][0],
+            os.path.getsize(os.path.join(HERE, "refsrc_rubberwhale_full_L1K3.npz")) // 1024), flush=True)
+    for name in ([a for a in sys.argv[1:] if a not in ("host_io", "rubberwhale", "rubberwhale_full")] or ([] if sys.argv[1:] else CASES)):
         t = time.time()
         out = run_case(name)
         path = os.path.join(HERE, "refsrc_%s.npz" % name)

@@ -229,6 +229,59 @@ def test_cuda_step_against_executed_source_on_rubberwhale(pkg, O):
         assert err.max() < 2e-4 and np.median(err) < 2e-6, (f, float(err.max()), float(np.median(err)))
 
 
+# ---- the same at FULL size: the whole 388 x 584 RubberWhale pair, one iteration of the executed source ---------------------------------
+def _rubberwhale_full(O):
+    d = np.load(os.path.join(GOLD, "refsrc_rubberwhale_full_L1K3.npz"))
+    I1, I2 = np.asfortranarray(d["I1"].astype(np.float64)), np.asfortranarray(d["I2"].astype(np.float64))
+    Mo, No = I1.shape
+    assert (Mo, No) == (388, 584)
+    rng = np.random.default_rng(int(d["seed"]))
+    draws = [rng.random(n).reshape(shp, order="F") for n, shp in ((1, (1, 1)),) + ((Mo * No, (Mo, No)),) * 4]
+    assert np.array_equal(np.array([x.sum() for x in draws]), d["draws_checksum"])
+    minu, maxu, minv, maxv = (float(x) for x in d["range"])
+    cfg = O.make_config(Mo, No, 1, 3, lambdas=5.0, epsn=0.001 ** 2, minu=minu, maxu=maxu, minv=minv, maxv=maxv)
+    w, ru, rv, su, sv = draws
+    shp = (Mo, No, 1)
+    st = O.State(minu + ru.reshape(shp) * (maxu - minu), minv + rv.reshape(shp) * (maxv - minv), su.reshape(shp) + (maxu - minu),
+                 sv.reshape(shp) + (maxv - minv), np.zeros(shp), np.zeros(shp + (2, 2)), np.ravel(w))
+    return d, cfg, I1, I2, st
+
+
+def test_oracle_reproduces_executed_source_on_full_rubberwhale(O):
+    d, cfg, I1, I2, st = _rubberwhale_full(O)
+    VV = O.get_vv(I2)
+    n, it, stopped, E, dm, ds = O.run(cfg, I1, VV, st, 1, 10 ** 6, 1)
+    assert abs(E[0] / d["Energy"][0] - 1) < 1e-13, (E[0], d["Energy"][0])
+    assert abs(dm[0] / float(d["p1_ptdmu"]) - 1) < 1e-12 and abs(ds[0] / float(d["p1_ptdsigma"]) - 1) < 1e-12
+    for f, name in (("muu", "muu"), ("muv", "muv"), ("sigu", "sigmau"), ("sigv", "sigmav"), ("pn", "pn"), ("rou", "rou")):
+        ref = d["p1_" + name]
+        _close(getattr(st, f)[::8, ::8].reshape(ref.shape), ref, 1e-10, f)
+    sums = np.array([getattr(st, f).sum() for f in ("muu", "muv", "sigu", "sigv", "pn", "rou")] +
+                    [(getattr(st, f) ** 2).sum() for f in ("muu", "muv", "sigu", "sigv", "pn", "rou")])
+    assert np.abs(sums / d["p1_sums"] - 1)[np.abs(d["p1_sums"]) > 0].max() < 1e-12
+    mp = np.concatenate([st.muu, st.muv], axis=2)
+    assert abs(O.profile_logp(cfg, I1, VV, mp) / d["logP"][0] - 1) < 1e-12
+
+
+@pytest.mark.gpu
+def test_cuda_step_against_executed_source_on_full_rubberwhale(pkg, O):
+    from test_gpu_parity import _round_state
+    d, cfg, I1, I2, st = _rubberwhale_full(O)
+    before = _round_state(st)
+    with pkg.Solver(options_from_cfg(cfg), I1, I2) as s:
+        s.set_state(state_dict(before), it=1, alpha=before.alpha)
+        r = s.step(1)
+        got = s.get_state()
+        lp = s.logp(s.map())
+    assert abs(r["Energy"][0] / d["Energy"][0] - 1) < 1e-5, (r["Energy"][0], d["Energy"][0])                 # north_star: 1e-4
+    assert abs(r["ptdmu"][0] / float(d["p1_ptdmu"]) - 1) < 1e-4 and abs(r["ptdsigma"][0] / float(d["p1_ptdsigma"]) - 1) < 1e-4
+    assert abs(lp / d["logP"][0] - 1) < 1e-5
+    for f in ("muu", "muv", "sigmau", "sigmav"):
+        ref = d["p1_" + f]
+        err = np.abs(got[f][::8, ::8].reshape(ref.shape) - ref)
+        assert err.max() < 5e-4 and np.median(err) < 2e-6, (f, float(err.max()), float(np.median(err)))
+
+
 # ---- host-side files of the drivers' path: readFlowFile.m, legacy/writeFlowFile.m, legacy/flowToColor.m (+ maxFlow) -----------
 def test_host_io_against_executed_source(pkg, O, tmp_path):
     d = np.load(os.path.join(GOLD, "refsrc_host_io.npz"))
