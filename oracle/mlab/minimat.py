@@ -33,7 +33,6 @@ class MatlabError(RuntimeError):
 KEYWORDS = {"function", "end", "if", "elseif", "else", "while", "for", "break", "return", "continue"}
 _num_re = re.compile(r"(\d+\.\d*|\d+|\.\d+)([eE][+-]?\d+)?")
 _id_re = re.compile(r"[A-Za-z_]\w*")
-_OPS3 = ("...",)
 _OPS2 = (".*", "./", ".^", ".'", "==", "~=", "<=", ">=", "&&", "||")
 _OPS1 = "+-*/^<>=&|~:,;()[]{}@.'\\"
 
@@ -697,6 +696,8 @@ def index_set(A, subs, value):
         idx = _sub_to_index(s, flat.size)
         if idx.size and idx.max() >= flat.size:
             raise MatlabError("growing an array by indexed assignment is not supported")
+        if not is_scalar(v) and arr(v).size != idx.size:
+            raise MatlabError("In an assignment A(I) = B, the number of elements in B and I must be the same (%d vs %d)" % (arr(v).size, idx.size))
         flat[idx] = v if is_scalar(v) else flatF(arr(v))
         return flat.reshape(A.shape, order="F")
     empty = A.size == 0

@@ -319,6 +319,27 @@ def test_host_io_live(pkg, O, tmp_path):
             assert all(np.array_equal(np.asarray(a), np.asarray(b)) for a, b in zip(src, other)), seq
 
 
+def test_reference_rejects_row_vector_flow_live(pkg, O):
+    """A finding, kept executable: the reference fails on a 1 x N flow field (N > 1) -- computeColor.m:57 indexes a column vector with
+    a row vector and gets a column back, so the arithmetic after it no longer conforms.  The compiled binary reports it through
+    Coder's run-time check, the .m source through MATLAB's assignment rule; the oracle and the product treat 1 x N like any field."""
+    sys.path.insert(0, GOLD)
+    import make_refsrc_golden as G
+    if not os.path.isdir(G.REF):
+        pytest.skip("reference tree not present on this box")
+    from oracle.mlab.minimat import Interp, MatlabError
+    from oracle.refbin import refbin
+    flow = np.asfortranarray(np.random.default_rng(0).normal(0, 1, (1, 7, 2)))
+    with pytest.raises(RuntimeError):
+        refbin.flowToColor_mex(flow)
+    with pytest.raises(MatlabError):
+        Interp([G.REF, os.path.join(G.REF, "legacy")]).call("flowToColor", flow, nargout=7)
+    a, b = O.flow_to_color(flow), pkg.flowToColor_mex(flow)
+    assert a[0].shape == (1, 7, 3) and np.array_equal(a[0], b[0])
+    col = np.asfortranarray(flow.transpose(1, 0, 2))                      # the transposed field is accepted by everyone and gives the same colours
+    assert np.array_equal(refbin.flowToColor_mex(col)[0].transpose(1, 0, 2), a[0])
+
+
 # ---- GPU: the CUDA path against the executed source ---------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", GPU_CASES)
