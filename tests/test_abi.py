@@ -107,3 +107,16 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".m")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle" not in txt.lower() or f in ("mex.h",), os.path.join(dp, f)
+
+
+def test_header_is_plain_c_and_usable(pkg, tmp_path):
+    """include/qgmap.h must be consumable from the reference's FFI language: a C99 program (examples/host_calls.c) compiles with
+    -pedantic -Werror against the header, links the shared library, exercises the host-side entry points and sees a compute call
+    either work (GPU box) or refuse with QGMAP_ERR_CUDA and the 'no CPU fallback' text."""
+    exe = str(tmp_path / "host_calls")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "host_calls.c"), "-L" + os.path.dirname(pkg.LIB_PATH), "-lqgmap", "-lm", "-o", exe])
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.dirname(pkg.LIB_PATH) + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([exe], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "host calls ok" in r.stdout and ("create refused" in r.stdout or "create ok" in r.stdout)
