@@ -99,6 +99,12 @@ A = [1 2; 3 4]; off = 10;
     end
 end
 """,
+    "afun3": """
+function out = afun3()
+S = cat(3, [1 2; 3 4], [10 20; 30 40]);   % 2 x 2 x 2 state next to a 2 x 2 index grid, as gqmap_gpu_mixture.m:29 does
+out = arrayfun(@(s, g) s * 100 + g, S, [1 2; 3 4]);
+end
+""",
     "misc": """
 function [a,b,c,d,e,f] = misc(o)
 a = [o.dir,'/',num2str(12),'.png'];
@@ -113,6 +119,39 @@ e = min(max(7, 1), 5);
 f = NaN(2,1); f(2) = 4;
 end
 """,
+    "more": """
+function [a,b,c,d,e,f,g,h] = more(varargin)
+a = numel(varargin); b = varargin{2};
+cellv = {'x', 'yz', 3};
+c = [cellv{2}, cellv{1}];                 % 'yzx'
+k = 10; add = @(x, y) x + y + k;          % captures k BY VALUE
+k = 1000;
+d = add(1, 2);                            % 13, not 1003
+s = struct('p', 2, 'q', [1 2 3]);
+s.r = s.p * 2;
+e = s.r + s.q(end);                       % 7
+G(:,:,2) = [1 2; 3 4];                    % created by indexed assignment, grows a zero first page
+f = size(G); g = G(:,:,1);
+name = 'dir/file.flo';
+idx = strfind(name, '.'); idx = idx(end);
+h = [name(idx:end), num2str(strcmp(name(idx:end), '.flo')), num2str(isfield(s, 'q')), num2str(ceil(2.1))];
+end
+""",
+    "cleanup": """
+function order = cleanup(n)
+order = inner(n);
+    function log = inner(n)
+        log = 0;
+        c1 = onCleanup(@() note(1));
+        c2 = onCleanup(@() note(2));
+        if n > 1, error('demo:fail', 'n was %d', n); end
+        log = 10;
+    end
+    function note(k)
+        order_sink(k);
+    end
+end
+""",
 }
 
 
@@ -120,6 +159,8 @@ end
 def interp(tmp_path_factory):
     root = tmp_path_factory.mktemp("mfiles")
     for name, src in PROGRAMS.items():
+        if name == "cleanup":
+            continue
         with open(os.path.join(root, name + ".m"), "w") as f:
             f.write(src.lstrip("\n"))
     return Interp([str(root)])
@@ -171,10 +212,53 @@ def test_arrayfun_with_nested_handle(interp):
     assert eq(p, [[11, 12], [16, 18]]) and eq(q, [[3, 2], [1, 1]])
 
 
+def test_arrayfun_expands_singleton_dimensions(interp):
+    out = interp.call("afun3")
+    assert out.shape == (2, 2, 2) and eq(out[:, :, 0], [[101, 202], [303, 404]]) and eq(out[:, :, 1], [[1001, 2002], [3003, 4004]])
+
+
 def test_strings_loops_builtins(interp):
     a, b, c, d, e, f = interp.call("misc", {"dir": "out"}, nargout=6)
     assert a == "out/12.png" and c == 2.0 and d == 5.0 and e == 5.0
     assert eq(b, [[1, 1, 2, 2], [1, 1, 2, 2], [3, 3, 4, 4], [3, 3, 4, 4]]) and np.isnan(f[0, 0]) and f[1, 0] == 4.0
+
+
+def test_cells_handles_structs_growth_strings(interp):
+    a, b, c, d, e, f, g, h = interp.call("more", 1.0, 7.0, 3.0, nargout=8)
+    assert (a, b, c, d, e) == (3.0, 7.0, "yzx", 13.0, 7.0)
+    assert eq(f, [[2, 2, 2]]) and eq(g, [[0, 0], [0, 0]]) and h == ".flo113"
+
+
+def test_oncleanup_runs_in_reverse_order_also_on_errors(tmp_path):
+    with open(tmp_path / "cleanup.m", "w") as f:
+        f.write(PROGRAMS["cleanup"].lstrip("\n"))
+    seen = []
+    I = Interp([str(tmp_path)], externals={"order_sink": lambda nargout, k: (seen.append(k), ())[1]})
+    assert I.call("cleanup", 1.0) == 10.0 and seen == [2.0, 1.0]
+    seen.clear()
+    with pytest.raises(MatlabError) as e:
+        I.call("cleanup", 5.0)
+    assert e.value.ident == "demo:fail" and "n was 5" in str(e.value) and seen == [2.0, 1.0]
+
+
+def test_scripts_and_file_io(tmp_path):
+    with open(tmp_path / "job.m", "w") as f:
+        f.write("clear;\nnames = {'a','b'};\nfor ti=1:numel(names)\n  opt.tag = names{ti}; opt.n = ti*2; % comment with 'quote\nend\n"
+                "fid = fopen(out, 'w'); fwrite(fid, 'PIEH'); fwrite(fid, [7 9], 'int32'); fwrite(fid, [1.5; -2], 'float32'); fclose(fid);\n"
+                "fid = fopen(out, 'r'); tag = fread(fid, 1, 'float32'); wh = fread(fid, 2, 'int32'); rest = fread(fid, inf, 'float32'); fclose(fid);\n"
+                "save('x.mat', 'opt', 'wh');\n")
+    I = Interp([str(tmp_path)])
+    saved = []
+    I.on_save = lambda fn, names, ws: saved.append((fn, names))
+    target = str(tmp_path / "t.bin")
+    # scripts share the caller's workspace in MATLAB; here the variable `out` is pre-seeded through a tiny wrapper script line
+    with open(tmp_path / "job.m") as f:
+        body = f.read()
+    with open(tmp_path / "job.m", "w") as f:
+        f.write("out = '%s';\n" % target + body.replace("clear;\n", ""))
+    ws = I.run_script(str(tmp_path / "job.m"))
+    assert ws["opt"] == {"tag": "b", "n": 4.0} and abs(ws["tag"] - 202021.25) < 1e-9 and eq(ws["wh"], [[7], [9]]) and eq(ws["rest"], [[1.5], [-2]])
+    assert saved == [("x.mat", ("opt", "wh"))] and open(target, "rb").read()[:4] == b"PIEH"
 
 
 def test_errors_are_loud(interp, tmp_path):
