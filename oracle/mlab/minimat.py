@@ -816,7 +816,7 @@ def _size(nargout, a, dim=None):
 
 
 def _arrayfun(interp, nargout, fh, *arrays):
-    if not isinstance(fh, FuncHandle):
+    if not isinstance(fh, (FuncHandle, AnonFunc)):
         raise MatlabError("arrayfun: first argument must be a function handle")
     arrays = [arr(a) for a in arrays]
     # gpuArray arrayfun expands singleton dimensions of its inputs (the reference passes M x N index grids next to M x N x L state)
