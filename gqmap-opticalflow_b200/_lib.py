@@ -36,7 +36,7 @@ class QgmapConfig(C.Structure):
         ("step0", C.c_double), ("step_tau", C.c_double), ("alpha_scale", C.c_double),
         ("T_floor", C.c_double), ("tor", C.c_double), ("sigma_step_scale", C.c_double),
         ("alpha_start", C.c_int32), ("alpha_mode", C.c_int32), ("anneal_every", C.c_int32),
-        ("device", C.c_int32), ("row_begin", C.c_int32), ("row_end", C.c_int32), ("log_every", C.c_int32),
+        ("device", C.c_int32), ("row_begin", C.c_int32), ("row_end", C.c_int32), ("log_every", C.c_int32), ("strip_rows", C.c_int32),
     ]
 
 
@@ -63,6 +63,8 @@ SIGNATURES = {
     "qgmap_get_map": (C.c_int, [C.c_void_p, _DP]),
     "qgmap_logp": (C.c_int, [C.c_void_p, _DP, _DP]),
     "qgmap_aepe": (C.c_int, [C.c_void_p, _DP, _DP, _U8P, _DP]),
+    "qgmap_set_truth": (C.c_int, [C.c_void_p, _DP, _U8P]),
+    "qgmap_monitor_partial": (C.c_int, [C.c_void_p, _DP, _DP]),
     "qgmap_solve": (C.c_int, [C.POINTER(QgmapConfig), _DP, _DP, C.c_int, C.c_int, C.c_int, C.POINTER(_DP), C.c_uint64,
                               _DP, _U8P, _DP, _DP, _DP, _DP, _DP, _DP, _IP]),
     "qgmap_group_solve": (C.c_int, [C.POINTER(QgmapConfig), _DP, _DP, C.c_int, C.c_int, C.c_int, C.c_int, _IP, C.POINTER(_DP), C.c_uint64,

@@ -2,6 +2,7 @@
 // iteration launches (CUDA graph of identical kernel nodes), monitoring, the one-call solver.
 #include "../../include/qgmap.h"
 #include "qgmap_iter.cuh"
+#include "qgmap_walk.cuh"
 #include "qgmap_internal.h"
 #include "qgmap_layout.cuh"
 
@@ -69,6 +70,7 @@ extern "C" int qgmap_config_defaults(qgmap_config *c, int variant)
 // --------------------------------------------------------------------------------------------------------------------
 template <int KT, bool SUPER, bool DUMP>
 static void launch_inst(const qgmap_handle *h) {
+    if (!SUPER && h->walk) { qgmap_walk_kernel<KT, DUMP><<<h->grid, 32, 0, h->stream>>>(h->params); return; }
     const dim3 block(QG_TW, QgTile<KT, SUPER>::TH + 1);
     if (h->lanes_per_belief == 4) qgmap_iter_kernel_g4<KT, SUPER, DUMP><<<h->grid, block, 0, h->stream>>>(h->params);
     else qgmap_iter_kernel<KT, SUPER, DUMP><<<h->grid, block, 0, h->stream>>>(h->params);
@@ -117,7 +119,7 @@ static void free_handle(qgmap_handle *h)
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->evb0) cudaEventDestroy(h->evb0);
     if (h->evb1) cudaEventDestroy(h->evb1);
-    void *ptrs[] = {h->I1f, h->VVf, h->I1d, h->VVd, h->buf[0], h->buf[1], h->dbg, h->ctrl, h->partials, h->hist[0],
+    void *ptrs[] = {h->I1f, h->VVf, h->I1d, h->VVd, h->buf[0], h->buf[1], h->dbg, h->ctrl, h->partials, h->gpartials, h->tickets, h->hist[0],
                     h->hist[1], h->hist[2], h->stage, h->mon_partials, h->d_map, h->d_tflow, h->d_unknown};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
@@ -153,6 +155,23 @@ static int ensure_hist(qgmap_handle *h, int its)
     h->params.hist_energy = h->hist[0]; h->params.hist_dmu = h->hist[1]; h->params.hist_dsig = h->hist[2];
     if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }     // params are baked into graph nodes
     return QGMAP_OK;
+}
+
+// Rows one warp of the row-walking kernel walks.  The halo edge above a strip costs about 0.15 of a row, so long strips are
+// cheap per row; but a launch is `strips / (SMs x resident warps)` waves and its last wave runs at whatever occupancy is left.
+// Rule: long strips (8 rows) when that still leaves >= 4 waves; otherwise the shortest strip that fits the whole launch into
+// ONE wave (every warp slot walks one strip, nothing is quantised), capped at 16 rows; QGMAP_STRIP_ROWS / cfg.strip_rows override.
+int qgmap_pick_strip_rows(int strips_x, int out_rows, int L, int sms, int K, int cfg_rows)
+{
+    if (const char *env = getenv("QGMAP_STRIP_ROWS")) { const int r = atoi(env); if (r >= 1) return std::min(r, 1 << 20); }
+    if (cfg_rows >= 1) return cfg_rows;
+    const int resident = (K == 3 || K == 5) ? QG_WALK_MINB : QG_WALK_MINB_BIGK;
+    const long long slots = (long long)sms * resident;
+    const long long rows = (long long)strips_x * out_rows * L;              // warp-rows of one launch
+    if (rows >= 4 * 8 * slots) return 8;
+    for (int r = 1; r <= 16; ++r)
+        if ((long long)strips_x * ((out_rows + r - 1) / r) * L <= slots) return r;
+    return 8;
 }
 
 extern "C" int qgmap_create(const qgmap_config *cfg, const double *I1, const double *I2, int Mo, int No, qgmap_handle **out)
@@ -241,6 +260,25 @@ extern "C" int qgmap_create(const qgmap_config *cfg, const double *I1, const dou
     const int tw = h->lanes_per_belief == 4 ? QG_CW - 1 : QG_TW - 1;
     const int th = qg_tile_rows(h->K, sup);
     h->grid = dim3((N - 2 + tw - 1) / tw, std::max((out_rows + th - 1) / th, 1), h->L);
+    // QGMAP_ITER=walk selects the row-walking form of the full-resolution kernel (qgmap_walk.cuh: one warp per strip of 31 columns
+    // x strip_rows rows, no CTA barrier; ~15% fewer instructions but it needs 96+ registers, measured 3-7% behind the tiled kernel
+    // on B200, profiles/r02_walk_ab.txt); default: the tiled kernel of qgmap_iter.cuh.
+    int strip_rows = 0;
+    {
+        const char *env = getenv("QGMAP_ITER");
+        h->walk = !sup && h->lanes_per_belief == 1 && env && !strcmp(env, "walk");
+        if (h->walk) {
+            int ndev_sm = 148;
+            cudaDeviceGetAttribute(&ndev_sm, cudaDevAttrMultiProcessorCount, h->device);
+            strip_rows = qgmap_pick_strip_rows(h->grid.x, std::max(out_rows, 1), h->L, ndev_sm, h->K, cfg->strip_rows);
+            h->grid = dim3(h->grid.x, std::max((out_rows + strip_rows - 1) / strip_rows, 1), h->L);
+            const size_t ngroups = (size_t)h->grid.y * h->grid.z;
+            QG_CUDA_C(cudaMalloc(&h->gpartials, ngroups * QG_NRED * sizeof(double)));
+            QG_CUDA_C(cudaMemsetAsync(h->gpartials, 0, ngroups * QG_NRED * sizeof(double), h->stream));
+            QG_CUDA_C(cudaMalloc(&h->tickets, ngroups * sizeof(unsigned int)));
+            QG_CUDA_C(cudaMemsetAsync(h->tickets, 0, ngroups * sizeof(unsigned int), h->stream));
+        }
+    }
     const size_t nblk = (size_t)h->grid.x * h->grid.y * h->grid.z;
     QG_CUDA_C(cudaMalloc(&h->partials, nblk * QG_NRED * sizeof(double)));
     QG_CUDA_C(cudaMemsetAsync(h->partials, 0, nblk * QG_NRED * sizeof(double), h->stream));
@@ -268,7 +306,7 @@ extern "C" int qgmap_create(const qgmap_config *cfg, const double *I1, const dou
     p.step0 = cfg->step0; p.step_tau = cfg->step_tau; p.alpha_scale = cfg->alpha_scale; p.drate = cfg->drate;
     p.sig_step = (float)cfg->sigma_step_scale; p.T_floor = cfg->T_floor; p.tor = cfg->tor; p.alpha_start = cfg->alpha_start; p.alpha_mode = cfg->alpha_mode;
     p.anneal_every = cfg->anneal_every;
-    p.ctrl = h->ctrl; p.partials = h->partials;
+    p.ctrl = h->ctrl; p.partials = h->partials; p.gpartials = h->gpartials; p.tickets = h->tickets; p.strip_rows = strip_rows;
     QG_CUDA_C(cudaStreamSynchronize(h->stream));
     if (ensure_hist(h, 1024) != QGMAP_OK) { free_handle(h); return QGMAP_ERR_CUDA; }
     QG_CUDA_C(cudaStreamSynchronize(h->stream));
@@ -429,7 +467,7 @@ static const int kGraphLen = 25;
 
 static int build_graph(qgmap_handle *h)
 {
-    if (h->graph || h->nranks > 1) return QGMAP_OK;
+    if (h->graph || (h->nranks > 1 && !qgmap_p2p_fused(h))) return QGMAP_OK;   // NCCL / publish-kernel bands: stream launches
     cudaGraph_t g = nullptr;
     QG_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
     for (int i = 0; i < kGraphLen; ++i) launch_iter(h, false);
@@ -461,6 +499,21 @@ int qgmap_prepare_step(qgmap_handle *h, int n, int its)
     return QGMAP_OK;
 }
 
+// n iterations of a single domain or of a peer-memory band on the handle's stream: CUDA graphs of kGraphLen identical kernel nodes
+// where one launch is one iteration (single domain; band with the exchange inside the row-walking kernel), stream launches else
+int qgmap_enqueue_iterations(qgmap_handle *h, int n, long long *launches)
+{
+    int left = n, rc;
+    if (h->nranks > 1 && !qgmap_p2p_fused(h)) {
+        for (; left > 0; --left) { if ((rc = qgmap_p2p_iteration(h, launches)) != QGMAP_OK) return rc; ++*launches; }
+        return QGMAP_OK;
+    }
+    if (left >= kGraphLen && (rc = build_graph(h)) != QGMAP_OK) return rc;
+    for (; left >= kGraphLen; left -= kGraphLen) { QG_CUDA(h, cudaGraphLaunch(h->graph, h->stream)); *launches += kGraphLen; }
+    for (; left > 0; --left) { launch_iter(h, false); ++*launches; }
+    return QGMAP_OK;
+}
+
 // enqueue up to n iterations on the handle's stream; returns without waiting
 extern "C" int qgmap_step_begin(qgmap_handle *h, int n, int its)
 {
@@ -468,17 +521,13 @@ extern "C" int qgmap_step_begin(qgmap_handle *h, int n, int its)
     int rc = qgmap_prepare_step(h, n, its);
     if (rc) return rc;
     long long launches = 0;
-    if (h->nranks <= 1 && n >= kGraphLen && (rc = build_graph(h)) != QGMAP_OK) return rc;   // host-side, before the timed region
+    if ((h->nranks <= 1 || qgmap_p2p_fused(h)) && n >= kGraphLen && (rc = build_graph(h)) != QGMAP_OK) return rc;   // host-side, before the timed region
     QG_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-    int left = n;
-    if (h->nranks > 1 && h->p2p) {                       // row band, exchange by our own kernel over peer memory (qgmap_p2p.cu)
-        qgmap_p2p_begin_step(h);
-        for (; left > 0; --left) { if ((rc = qgmap_p2p_iteration(h, &launches)) != QGMAP_OK) return rc; ++launches; }
-    } else if (h->nranks > 1) {                          // row band over NCCL (qgmap_band.cu)
-        for (; left > 0; --left) { if ((rc = qgmap_band_iteration(h, &launches)) != QGMAP_OK) return rc; ++launches; }
+    if (h->nranks > 1 && !h->p2p) {                      // row band over NCCL (qgmap_band.cu)
+        for (int left = n; left > 0; --left) { if ((rc = qgmap_band_iteration(h, &launches)) != QGMAP_OK) return rc; ++launches; }
     } else {
-        for (; left >= kGraphLen; left -= kGraphLen) { QG_CUDA(h, cudaGraphLaunch(h->graph, h->stream)); launches += kGraphLen; }
-        for (; left > 0; --left) { launch_iter(h, false); ++launches; }
+        if (h->nranks > 1) qgmap_p2p_begin_step(h);      // row band, exchange by our own kernels over peer memory (qgmap_p2p.cu)
+        if ((rc = qgmap_enqueue_iterations(h, n, &launches)) != QGMAP_OK) return rc;
     }
     QG_CUDA(h, cudaGetLastError());
     QG_CUDA(h, cudaEventRecord(h->ev1, h->stream));
@@ -634,6 +683,7 @@ static QgMonArgs mon_params(const qgmap_handle *h)
     q.I1 = h->I1d; q.pitchI = h->pitchI; q.VV = h->VVd; q.pitchV = h->pitchV;
     q.Mo = h->Mo; q.No = h->No; q.M = h->M; q.N = h->N; q.super = h->cfg.variant == QGMAP_VARIANT_SUPER;
     q.lambdad = h->cfg.lambdad; q.lambdas = h->cfg.lambdas; q.epsn = h->cfg.epsn;
+    q.r0 = 0; q.r1 = h->M;
     return q;
 }
 
@@ -643,8 +693,10 @@ static int ensure_map(qgmap_handle *h)
     return QGMAP_OK;
 }
 
-// MAP of the current beliefs into h->d_map (device, column-major M x N x 2)
-static int map_device(qgmap_handle *h)
+// MAP of the current beliefs into h->d_map (device, column-major M x N x 2): the rows the handle owns, or (stored = true) every
+// row it stores -- a band's halo rows carry the neighbours' current beliefs, so the band can evaluate its own share of
+// profile_logP without seeing anybody else's map
+static int map_device(qgmap_handle *h, bool stored = false)
 {
     int rc = ensure_map(h);
     if (rc) return rc;
@@ -653,7 +705,7 @@ static int map_device(qgmap_handle *h)
     const long long fs = (long long)h->L * h->plane;
     const long long tot = 2LL * h->M * h->N;
     qgmap_launch_find_map_f32(&h->ctrl->alpha[0], b + F_MUU * fs, b + F_SIGU * fs, b + F_MUV * fs, b + F_SIGV * fs, h->plane,
-                              h->M, h->N, h->L, h->P, h->g0, h->row_begin, h->row_end, h->d_map, tot, h->stream);
+                              h->M, h->N, h->L, h->P, h->g0, stored ? h->g0 : h->row_begin, stored ? h->g1 : h->row_end, h->d_map, tot, h->stream);
     QG_CUDA(h, cudaGetLastError());
     return QGMAP_OK;
 }
@@ -739,6 +791,44 @@ extern "C" int qgmap_aepe(qgmap_handle *h, const double *map, const double *tflo
     if ((rc = upload_truth(h, tflow, unknown)) != QGMAP_OK) return rc;
     QG_CUDA(h, cudaMemcpyAsync(h->d_map, map, (size_t)h->M * h->N * 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     return aepe_device(h, h->d_map, aepe);
+}
+
+extern "C" int qgmap_set_truth(qgmap_handle *h, const double *tflow, const uint8_t *unknown)
+{
+    if (!h || !tflow) return QGMAP_ERR_ARG;
+    QG_CUDA(h, cudaSetDevice(h->device));
+    int rc = upload_truth(h, tflow, unknown);
+    if (rc) return rc;
+    QG_CUDA(h, cudaStreamSynchronize(h->stream));
+    return QGMAP_OK;
+}
+
+// Monitoring block :52-68 for the rows this handle OWNS, entirely on its device: MAP of the stored rows, the handle's share of
+// profile_logP (:148-154; the edges that start in an owned row) and of the AEPE numerator (:63-64).  A row-band run adds the shares
+// in band order and divides the AEPE sum by (Mo-2b)(No-2b); for a whole-grid handle the shares are the totals.
+extern "C" int qgmap_monitor_partial(qgmap_handle *h, double *logp_share, double *aepe_sum_share)
+{
+    if (!h) return QGMAP_ERR_ARG;
+    if (!h->has_state) QG_FAIL(h, QGMAP_ERR_STATE, "qgmap_monitor_partial: no state set");
+    if (aepe_sum_share && !h->d_tflow) QG_FAIL(h, QGMAP_ERR_STATE, "qgmap_monitor_partial: AEPE asked for before qgmap_set_truth");
+    QG_CUDA(h, cudaSetDevice(h->device));
+    int rc = sync_ctrl(h);
+    if (rc) return rc;
+    if ((rc = map_device(h, true)) != QGMAP_OK) return rc;
+    QgMonArgs q = mon_params(h);
+    q.r0 = h->row_begin; q.r1 = h->row_end;
+    const int nblk = 592;
+    if (logp_share) {
+        qgmap_launch_logp(q, h->d_map, h->mon_partials, nblk, h->stream);
+        QG_CUDA(h, cudaGetLastError());
+        if ((rc = reduce_partials(h, nblk, logp_share)) != QGMAP_OK) return rc;
+    }
+    if (aepe_sum_share) {
+        qgmap_launch_aepe(q, h->d_map, h->d_tflow, h->has_unknown ? h->d_unknown : nullptr, h->mon_partials, nblk, h->stream);
+        QG_CUDA(h, cudaGetLastError());
+        if ((rc = reduce_partials(h, nblk, aepe_sum_share)) != QGMAP_OK) return rc;
+    }
+    return QGMAP_OK;
 }
 
 extern "C" int qgmap_debug_gradients(qgmap_handle *h, double *G_muu, double *G_muv, double *G_sigu, double *G_sigv,
@@ -914,7 +1004,10 @@ extern "C" int qgmap_group_solve(const qgmap_config *cfg, const double *I1, cons
         if (Energy) Energy[i] = 0.0;
         if (logP) logP[i] = nan;
     }
-    qgmap_handle *h0 = qgmap_group_band(g, 0);                                       // monitoring kernels run on band 0's device
+    qgmap_handle *h0 = qgmap_group_band(g, 0);                                       // the PNG dump is rendered from band 0's device
+    if (tflow && AEPE)
+        for (int b = 0; b < nbands; ++b)
+            if ((rc = qgmap_set_truth(qgmap_group_band(g, b), tflow, unknown)) != QGMAP_OK) { g_last_error = qgmap_group_band(g, b)->err; return bail(rc); }
     const int every = cfg->log_every > 0 ? cfg->log_every : 300;
     int it = 1, stopped = 0;
     float ms = 0.f;
@@ -930,15 +1023,31 @@ extern "C" int qgmap_group_solve(const qgmap_config *cfg, const double *I1, cons
         it += done;
         const int last = it - 1;
         if (done > 0 && (last == 1 || last % every == 0) && (AEPE || logP || !g_dump_dir.empty())) {     // :52-68
-            for (int b = 0; b < nbands; ++b) {                                                       // every band extracts the MAP of its
-                qgmap_handle *hb = qgmap_group_band(g, b);                                           // own rows on its own GPU (:52-58)
-                if ((rc = qgmap_get_map(hb, map.data())) != QGMAP_OK) { g_last_error = hb->err; return bail(rc); }
+            // every band extracts the MAP of the rows it stores and sums its own share of logP / AEPE on its own GPU (:52-67);
+            // only the scalars travel.  The colour-coded PNG (:59-62) needs the whole map: gathered only when options.dir is set.
+            double lp = 0.0, ae = 0.0;
+            const bool want_ae = tflow && AEPE;
+            for (int b = 0; b < nbands; ++b) {
+                qgmap_handle *hb = qgmap_group_band(g, b);
+                double lpb = 0.0, aeb = 0.0;
+                if ((rc = qgmap_monitor_partial(hb, logP ? &lpb : nullptr, want_ae ? &aeb : nullptr)) != QGMAP_OK) { g_last_error = hb->err; return bail(rc); }
+                lp += lpb; ae += aeb;                                                                    // fixed band order
             }
-            double lp = nan;
-            if ((rc = qgmap_logp(h0, map.data(), &lp)) != QGMAP_OK) { g_last_error = h0->err; return bail(rc); }   // also stages the map on h0
             if (logP) logP[last - 1] = lp;
-            if (!g_dump_dir.empty() && (rc = dump_map_png(h0, last)) != QGMAP_OK) { g_last_error = h0->err; return bail(rc); }
-            if (tflow && AEPE && (rc = qgmap_aepe(h0, map.data(), tflow, unknown, &AEPE[last - 1])) != QGMAP_OK) { g_last_error = h0->err; return bail(rc); }
+            if (want_ae) {
+                const int bw = cfg->variant == QGMAP_VARIANT_SUPER ? 4 : 1;
+                AEPE[last - 1] = ae / ((double)(Mo - 2 * bw) * (double)(No - 2 * bw));
+            }
+            if (!g_dump_dir.empty()) {
+                for (int b = 0; b < nbands; ++b) {
+                    qgmap_handle *hb = qgmap_group_band(g, b);
+                    if ((rc = qgmap_get_map(hb, map.data())) != QGMAP_OK) { g_last_error = hb->err; return bail(rc); }
+                }
+                QG_CUDA(h0, cudaSetDevice(h0->device));
+                if ((rc = ensure_map(h0)) != QGMAP_OK) return bail(rc);
+                QG_CUDA(h0, cudaMemcpyAsync(h0->d_map, map.data(), map.size() * sizeof(double), cudaMemcpyHostToDevice, h0->stream));
+                if ((rc = dump_map_png(h0, last)) != QGMAP_OK) { g_last_error = h0->err; return bail(rc); }
+            }
         }
         if (done < n) break;
     }

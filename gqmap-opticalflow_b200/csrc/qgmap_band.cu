@@ -259,7 +259,10 @@ extern "C" int qgmap_group_create(const qgmap_config *cfg, const double *I1, con
     bool distinct = nbands > 1;
     for (int a = 0; a < nbands && distinct; ++a)
         for (int b = a + 1; b < nbands; ++b) if (g->bands[a]->device == g->bands[b]->device) distinct = false;
-    if (const char *env = getenv("QGMAP_GROUP_TRANSPORT")) { if (!strcmp(env, "events")) distinct = false; else if (!strcmp(env, "p2p") && nbands > 1) distinct = true; }
+    // QGMAP_GROUP_TRANSPORT=events forces the copies; =p2p-shared (tests only) runs the peer-memory kernels although bands share a
+    // GPU -- their flag waits then rely on the device running the bands' streams concurrently (they time out into QGMAP_ERR_COMM
+    // under a serialising tool).  A plain "p2p" never overrides the shared-GPU rule.
+    if (const char *env = getenv("QGMAP_GROUP_TRANSPORT")) { if (!strcmp(env, "events")) distinct = false; else if (!strcmp(env, "p2p-shared") && nbands > 1) distinct = true; }
     if (distinct && nbands <= QGMAP_P2P_RANKS_MAX) {
         std::vector<char> blobs((size_t)nbands * QGMAP_P2P_BLOB_BYTES);
         for (int b = 0; b < nbands; ++b) { int rc = qgmap_band_p2p_export(g->bands[b], blobs.data() + (size_t)b * QGMAP_P2P_BLOB_BYTES); if (rc) return bail(rc); }
@@ -330,15 +333,24 @@ extern "C" int qgmap_group_step(qgmap_group *g, int n, int its, double *energy, 
     QGB_CUDA(h0, cudaEventRecord(g->ev0, h0->stream));
     for (int b = 1; b < nb; ++b) { cudaSetDevice(g->bands[b]->device); QGB_CUDA(g->bands[b], cudaStreamWaitEvent(g->bands[b]->stream, g->ev0, 0)); }
     if (g->p2p) {
-        for (qgmap_handle *h : g->bands) qgmap_p2p_begin_step(h);
-        for (int k = 0; k < n; ++k)
-            for (int b = 0; b < nb; ++b) {
-                qgmap_handle *h = g->bands[b];
+        for (qgmap_handle *h : g->bands) { QGB_CUDA(h, cudaSetDevice(h->device)); qgmap_p2p_begin_step(h); }
+        if (qgmap_p2p_fused(h0)) {                                          // one launch per iteration: each band's stream gets its
+            for (qgmap_handle *h : g->bands) {                             // whole run (graphs); the kernels pace each other by flags
                 long long nl = 0;
                 QGB_CUDA(h, cudaSetDevice(h->device));
-                int rc = qgmap_p2p_iteration(h, &nl);
+                int rc = qgmap_enqueue_iterations(h, n, &nl);
                 if (rc) { g->err = h->err; return rc; }
             }
+        } else {
+            for (int k = 0; k < n; ++k)
+                for (int b = 0; b < nb; ++b) {
+                    qgmap_handle *h = g->bands[b];
+                    long long nl = 0;
+                    QGB_CUDA(h, cudaSetDevice(h->device));
+                    int rc = qgmap_p2p_iteration(h, &nl);
+                    if (rc) { g->err = h->err; return rc; }
+                }
+        }
     }
     for (int k = 0; k < (g->p2p ? 0 : n); ++k) {
         const int wbuf = (it_start + k) & 1;                               // buffer written by this iteration

@@ -126,7 +126,8 @@ struct QgIterParams {
     int g0;                            // global row index of local row 0 (band storage)
     int out_r0, out_r1;                // global rows [out_r0,out_r1) this handle updates
     int K;                             // quadrature order (runtime copy)
-    int band;                          // 1: defer control update to the finalize kernel (after all-reduce)
+    int band;                          // 1: leave the band's partial sums in ctrl->sums (a later kernel all-reduces them and advances
+                                       // the control block); 2: exchange rows and sums with the peers inside the iteration kernel
     float lambdad, lambdas, epsn;
     float minu, maxu, minv, maxv, sig_min, sig_max, corr_tor, sig_step;
     double step0, step_tau;
@@ -134,6 +135,11 @@ struct QgIterParams {
     int alpha_start, alpha_mode, anneal_every;
     QgCtrl *ctrl;
     double *partials;                  // [nblocks][QG_NRED]
+    double *gpartials;                 // row-walking kernel: [strip rows x L][QG_NRED], second reduction level
+    unsigned int *tickets;             // row-walking kernel: [strip rows x L] finished-strip counters
+    int strip_rows;                    // row-walking kernel: rows one warp walks
+    int pub_row[2];                    // band == 2: global row whose updated beliefs also go to the band above [0] / below [1]; -1 = none
+    const struct QgPeer *peer;         // band == 2: peer-memory exchange fused into the row-walking kernel (qgmap_peer.cuh)
     double *hist_energy, *hist_dmu, *hist_dsig;   // its entries each, index it-1
     float *dbg;                        // DUMP: 11 fields x L planes
     QgTables tab;
@@ -523,4 +529,154 @@ __device__ __forceinline__ void qg_edge2(const QgTables &tab, int Krt, float a, 
     QgMoments mv = {E.y * sc, MI.y * sc, MJ.y * sc, MII.y * sc, MJJ.y * sc, MB.y * sc};
     gu = qg_epilogue(mu, su, a, o1.x, o2.x, p.x, T);
     gv = qg_epilogue(mv, sv, a, o1.y, o2.y, p.y, T);
+}
+
+// ---- packed epilogue: both flow layers of one edge direction at once (.x = u layer, .y = v layer); gqmap_gpu_mixture.m:137-145.
+struct QgSpectral2 {
+    float2 s, t, pr, q, c1, c2;
+    __device__ __forceinline__ void set(float2 p) {
+        const float2 one = qg_bc(1.0f);
+        const float2 omp = qg_sub2(one, p), opp = qg_add2(one, p);
+        const float2 sp = make_float2(qg_sqrt(opp.x), qg_sqrt(opp.y)), sm = make_float2(qg_sqrt(omp.x), qg_sqrt(omp.y));
+        s = qg_mul2(qg_add2(sp, sm), qg_bc(0.5f));
+        t = qg_mul2(qg_sub2(sp, sm), qg_bc(0.5f));
+        pr = qg_mul2(omp, opp);
+        q = qg_mul2(sp, sm);
+        // c1 = s - p*t, c2 = t - p*s without cancellation (see QgSpectral::set): p >= 0: c1 = t*omp + sm, c2 = s*omp - sm;
+        // p < 0: c1 = -t*opp + sp, c2 = -s*opp + sp.  Select the operands per layer, then two packed FMAs.
+        const bool px = p.x >= 0.0f, py = p.y >= 0.0f;
+        const float2 A = make_float2(px ? omp.x : opp.x, py ? omp.y : opp.y);
+        const float2 B = make_float2(px ? sm.x : sp.x, py ? sm.y : sp.y);
+        const float2 sg = make_float2(px ? 1.0f : -1.0f, py ? 1.0f : -1.0f);
+        c1 = qg_fma2(qg_mul2(sg, t), A, B);
+        c2 = qg_fma2(qg_mul2(sg, s), A, qg_neg2(qg_mul2(sg, B)));
+    }
+};
+
+struct QgGrad2 { float2 da, du1, du2, do1, do2, dp, Ei; };
+
+// m*: moments of the POTENTIAL already scaled by -lambda/pi.  kT = +T for edges.
+__device__ __forceinline__ QgGrad2 qg_epilogue2(float2 E, float2 MI, float2 MJ, float2 MII, float2 MJJ, float2 MB, const QgSpectral2 &sp,
+                                                float a, float2 o1, float2 o2, float2 p, float kT)
+{
+    const float sqrt2 = 1.4142135623730951f, const1 = 2.8378770664093453f;   // 1+log(2pi)
+    QgGrad2 g;
+    const float2 A = qg_add2(MII, MJJ), D = qg_sub2(MII, MJJ);
+    const float2 S1 = qg_fma2(sp.c1, MI, qg_mul2(sp.c2, MJ));
+    const float2 S2 = qg_fma2(sp.c2, MI, qg_mul2(sp.c1, MJ));
+    const float2 EmA = qg_sub2(E, A);
+    const float2 Sp = qg_fma2(p, EmA, qg_add2(MB, MB));
+    const float2 Dq = qg_mul2(D, make_float2(qg_rcp(sp.q.x), qg_rcp(sp.q.y)));
+    const float2 T1 = qg_sub2(Dq, EmA), T2 = qg_neg2(qg_add2(Dq, EmA));
+    const float2 ipr = make_float2(qg_rcp(sp.pr.x), qg_rcp(sp.pr.y));
+    const float2 io1 = make_float2(qg_rcp(o1.x), qg_rcp(o1.y)), io2 = make_float2(qg_rcp(o2.x), qg_rcp(o2.y));
+    const float2 a2 = qg_bc(a), kT2 = qg_bc(kT);
+    const float2 as = qg_mul2(qg_mul2(a2, qg_bc(sqrt2)), ipr);
+    g.du1 = qg_mul2(qg_mul2(as, S1), io1);
+    g.du2 = qg_mul2(qg_mul2(as, S2), io2);
+    float2 H = qg_bc(0.0f);
+    if (kT != 0.0f) {
+        const float2 arg = qg_mul2(qg_mul2(sp.q, o1), o2);
+        H = make_float2(const1 + logf(arg.x), const1 + logf(arg.y));
+    }
+    g.da = qg_fma2(kT2, H, E);
+    g.do1 = qg_mul2(qg_mul2(a2, qg_add2(T1, kT2)), io1);
+    g.do2 = qg_mul2(qg_mul2(a2, qg_add2(T2, kT2)), io2);
+    g.dp = qg_mul2(qg_mul2(a2, qg_fma2(qg_neg2(kT2), p, Sp)), ipr);
+    g.Ei = qg_mul2(a2, g.da);
+    return g;
+}
+
+// Two edge quadratures at once (u and v layer of one direction), :118-146; as qg_edge2 with the packed epilogue.
+template <int KT>
+__device__ __forceinline__ QgGrad2 qg_edge2p(const QgTables &tab, int Krt, float a, float2 u1, float2 u2, float2 o1, float2 o2, float2 p,
+                                             float lambdas, float epsn, float T)
+{
+    const float sqrt2 = 1.4142135623730951f, invpi = 0.31830988618379067f;
+    const int K = KT > 0 ? KT : Krt;
+    QgSpectral2 sp;
+    sp.set(p);
+    const float2 r2 = qg_bc(sqrt2);
+    const float2 A = qg_mul2(r2, qg_sub2(qg_mul2(o1, sp.s), qg_mul2(o2, sp.t)));
+    const float2 B = qg_mul2(r2, qg_sub2(qg_mul2(o1, sp.t), qg_mul2(o2, sp.s)));
+    const float2 d0 = qg_sub2(u1, u2), eps2 = qg_bc(epsn), zero = qg_bc(0.0f);
+    float2 E = zero, MI = zero, MJ = zero, MII = zero, MJJ = zero, MB = zero;
+#pragma unroll 1
+    for (int r = 0; r < K; ++r) {
+        const float2 dr = qg_fma2(B, qg_bc(tab.X[r]), d0);
+        float2 S0 = zero, S1 = zero, S2 = zero;
+        if (KT > 0) {
+#pragma unroll
+            for (int c = 0; c < (KT > 0 ? KT : 1); ++c) {
+                const float2 d = qg_fma2(A, qg_bc(tab.X[c]), dr);
+                const float2 q = qg_fma2(d, d, eps2);
+                const float2 f = make_float2(qg_sqrt(q.x), qg_sqrt(q.y));
+                S0 = qg_fma2(f, qg_bc(tab.W[c]), S0);
+                S1 = qg_fma2(f, qg_bc(tab.WX[c]), S1);
+                S2 = qg_fma2(f, qg_bc(tab.WXX[c]), S2);
+            }
+        } else {
+#pragma unroll 1
+            for (int c = 0; c < K; ++c) {
+                const float2 d = qg_fma2(A, qg_bc(tab.X[c]), dr);
+                const float2 q = qg_fma2(d, d, eps2);
+                const float2 f = make_float2(qg_sqrt(q.x), qg_sqrt(q.y));
+                S0 = qg_fma2(f, qg_bc(tab.W[c]), S0);
+                S1 = qg_fma2(f, qg_bc(tab.WX[c]), S1);
+                S2 = qg_fma2(f, qg_bc(tab.WXX[c]), S2);
+            }
+        }
+        const float wr = tab.W[r], wxr = tab.WX[r], wxxr = tab.WXX[r];
+        E = qg_fma2(S0, qg_bc(wr), E);
+        MI = qg_fma2(S1, qg_bc(wr), MI);
+        MII = qg_fma2(S2, qg_bc(wr), MII);
+        MJ = qg_fma2(S0, qg_bc(wxr), MJ);
+        MB = qg_fma2(S1, qg_bc(wxr), MB);
+        MJJ = qg_fma2(S0, qg_bc(wxxr), MJJ);
+    }
+    const float2 sc = qg_bc(-lambdas * invpi);
+    return qg_epilogue2(qg_mul2(E, sc), qg_mul2(MI, sc), qg_mul2(MJ, sc), qg_mul2(MII, sc), qg_mul2(MJJ, sc), qg_mul2(MB, sc), sp, a,
+                        o1, o2, p, T);
+}
+
+// Node sample for a belief whose whole quadrature cloud lies inside the image: the clamps of :157-162 cannot fire, so the
+// cell is addressed RELATIVE to the belief's own pixel (vv_mn = &VV8[m*pitchV + n]) and neither m nor n is live in the loop.
+// The tap cache is keyed on the raw bits of the magic-number floor (equal bits <=> equal cell); the two 256-bit loads are
+// predicated PTX, so the reload is never a branch and lanes that keep their cell keep their registers.
+struct QgTapCacheRel {
+    int kx, ky;
+    QgTap8 v01, v23;
+    __device__ __forceinline__ QgTapCacheRel() : kx(0), ky(0) {}     // 0 is not a valid key (keys are 0x4B400000 + small int)
+};
+__device__ __forceinline__ float qg_node_sample_inside(const QgTap8 *__restrict__ vv_mn, int pitchV, int koff, long long rowskip, float2 x,
+                                                       float I1v, float epsn, QgTapCacheRel &tc)
+{
+    const float2 magic = qg_bc(12582912.0f);
+    const float2 t = qg_add2_rm(x, magic);                            // floor(x) in the mantissa (qg_floor_split2)
+    const float2 fr = qg_sub2(x, qg_sub2(t, magic));
+    const int kx = __float_as_int(t.x), ky = __float_as_int(t.y);
+    const int reload = (kx != tc.kx) | (ky != tc.ky);
+    tc.kx = kx; tc.ky = ky;
+    // (ky-C)*pitch + (kx-C) = ky*pitch + kx + koff; the address arithmetic is unconditional (five integer instructions), only
+    // the two loads are predicated: lanes that keep their cell keep their registers
+    const QgTap8 *a0 = vv_mn + (ky * pitchV + kx + koff);
+    const QgTap8 *a1 = reinterpret_cast<const QgTap8 *>(reinterpret_cast<const char *>(a0) + rowskip);
+    asm("{\n\t.reg .pred q;\n\t"
+        "setp.ne.s32 q, %18, 0;\n\t"
+        "@q ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%16];\n\t"
+        "@q ld.global.nc.v8.f32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%17];\n\t}"
+        : "+f"(tc.v01.p[0].x), "+f"(tc.v01.p[0].y), "+f"(tc.v01.p[1].x), "+f"(tc.v01.p[1].y), "+f"(tc.v01.p[2].x), "+f"(tc.v01.p[2].y),
+          "+f"(tc.v01.p[3].x), "+f"(tc.v01.p[3].y), "+f"(tc.v23.p[0].x), "+f"(tc.v23.p[0].y), "+f"(tc.v23.p[1].x), "+f"(tc.v23.p[1].y),
+          "+f"(tc.v23.p[2].x), "+f"(tc.v23.p[2].y), "+f"(tc.v23.p[3].x), "+f"(tc.v23.p[3].y)
+        : "l"(a0), "l"(a1), "r"(reload));
+    float2 n0, w1, w2, n3;
+    qg_cubic_w2(fr, n0, w1, w2, n3);
+    float2 h01 = qg_mul2(tc.v01.p[0], qg_bc(-n0.x));
+    float2 h23 = qg_mul2(tc.v23.p[0], qg_bc(-n0.x));
+    h01 = qg_fma2(tc.v01.p[1], qg_bc(w1.x), h01);  h23 = qg_fma2(tc.v23.p[1], qg_bc(w1.x), h23);
+    h01 = qg_fma2(tc.v01.p[2], qg_bc(w2.x), h01);  h23 = qg_fma2(tc.v23.p[2], qg_bc(w2.x), h23);
+    h01 = qg_fma2(tc.v01.p[3], qg_bc(-n3.x), h01); h23 = qg_fma2(tc.v23.p[3], qg_bc(-n3.x), h23);
+    const float v = fmaf(h23.y, -n3.y, fmaf(h23.x, w2.y, fmaf(h01.y, w1.y, h01.x * -n0.y)));
+    const float d = fmaf(-0.25f, v, I1v);
+    return qg_sqrt(fmaf(d, d, epsn));
 }

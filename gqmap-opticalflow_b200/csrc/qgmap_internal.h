@@ -29,7 +29,9 @@ struct qgmap_handle {
     float *buf[2] = {nullptr, nullptr};
     float *dbg = nullptr;
     QgCtrl *ctrl = nullptr, *ctrl_host = nullptr;
-    double *partials = nullptr;
+    double *partials = nullptr, *gpartials = nullptr;
+    unsigned int *tickets = nullptr;
+    bool walk = false;            // full-resolution variant: row-walking kernel (qgmap_walk.cuh) instead of the tiled one
     double *hist[3] = {nullptr, nullptr, nullptr};
     int hist_cap = 0;
     double *stage = nullptr;
@@ -61,6 +63,7 @@ void qgmap_launch_find_map_f64(const double *alpha, const double *mu_u, const do
 struct QgMonArgs {
     const double *I1; int pitchI; const double *VV; int pitchV;
     int Mo, No, M, N, super; double lambdad, lambdas, epsn;
+    int r0, r1;                    // belief rows [r0,r1) summed (a band's share)
 };
 void qgmap_launch_logp(const QgMonArgs &q, const double *uv, double *partials, int nblk, cudaStream_t s);
 void qgmap_launch_aepe(const QgMonArgs &q, const double *map, const double *tflow, const unsigned char *unknown,
@@ -74,7 +77,9 @@ void qgmap_launch_iteration(const qgmap_handle *h);             // plain iterati
 void qgmap_launch_advance(const qgmap_handle *h);
 void qgmap_p2p_release(qgmap_handle *h);
 void qgmap_p2p_begin_step(qgmap_handle *h);                     // new generation tag for the flags of this qgmap_step call
-int qgmap_p2p_iteration(qgmap_handle *h, long long *launches);  // iteration kernel + publish/advance kernel
+int qgmap_p2p_iteration(qgmap_handle *h, long long *launches);  // iteration kernel (+ publish/advance kernel for the tiled form)
+bool qgmap_p2p_fused(const qgmap_handle *h);                    // exchange inside the iteration kernel (row-walking form)
+int qgmap_enqueue_iterations(qgmap_handle *h, int n, long long *launches);   // n iterations of a single domain or a p2p band
 int qgmap_prepare_step(qgmap_handle *h, int n, int its);
 int qgmap_finish_step(qgmap_handle *h, double *energy, double *ptdmu, double *ptdsigma, int *n_done, int *stopped);
 void qgmap_set_last_error(const char *msg);

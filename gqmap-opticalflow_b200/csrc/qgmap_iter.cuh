@@ -13,6 +13,7 @@
 #pragma once
 #include "qgmap_device.cuh"
 #include "qgmap_advance.cuh"
+#include "qgmap_peer.cuh"
 
 __device__ __forceinline__ float qg_clamp(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 
@@ -86,13 +87,32 @@ __device__ __forceinline__ void qg_block_finish(const QgIterParams &p, QgCtrl *c
         }
         __syncthreads();
     }
-    if (tid == 0) {
-        ctrl->ticket = 0;
+    if (tid == 0) ctrl->ticket = 0;
+    if (p.band == 2) {                       // row band over peer memory: post, wait for the other bands, add in rank order, advance
+        if (tid < 32) qg_peer_finish(p, ctrl, p.peer, sh_sum, tid);
+    } else if (tid == 0) {
         if (p.band) {
             for (int k = 0; k < p.L * QG_NRED; ++k) ctrl->sums[k] = sh_sum[k];   // summed across bands / ranks, then
         } else {                                                               // the advance kernel runs qg_advance
             qg_advance(p, ctrl, sh_sum);
         }
+    }
+}
+
+// Row band over peer memory (QgIterParams::band == 2): the updated beliefs of the band's first / last row also go straight into
+// the neighbouring band's halo row of the same ping-pong buffer (NVLink stores; qgmap_peer.cuh).  f0..f0+nf-1: fields to copy.
+__device__ __forceinline__ void qg_publish_row(const QgIterParams &p, int it, int m, int n, int l, const float *o, long long fstr,
+                                               int f0, int nf)
+{
+    const QgPeer *q = p.peer;
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+        float *nb = side ? q->dn[it & 1] : q->up[it & 1];
+        if (!nb || m != p.pub_row[side]) continue;
+        const long long npl = side ? q->dn_plane : q->up_plane;
+        float *t = nb + (side ? q->dn_off : q->up_off) + n + (long long)l * npl;
+        const long long nfs = (long long)p.L * npl;
+        for (int f = f0; f < f0 + nf; ++f) t[f * nfs] = o[f * fstr];
     }
 }
 
@@ -134,7 +154,7 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
         sigu = qg_lds(base + F_SIGU * fstr + idx); sigv = qg_lds(base + F_SIGV * fstr + idx);
     }
 
-    QgGrad gdu = {}, gdv = {}, gru = {}, grv = {};
+    QgGrad2 gd = {}, gr = {};
     float rou0 = 0.f, rou1 = 0.f, rou2 = 0.f, rou3 = 0.f;
 
     // ---- down edge (m,n)->(m+1,n), layers u and v as one fp32x2 stream  (:31-34, e=1) ----------------------------------
@@ -142,57 +162,74 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
         const long long idn = idx + p.P;
         rou0 = qg_lds(base + F_ROU0 * fstr + idx);
         rou2 = qg_lds(base + F_ROU2 * fstr + idx);
-        qg_edge2<KT>(p.tab, p.K, a, make_float2(muu, muv),
-                     make_float2(qg_lds(base + F_MUU * fstr + idn), qg_lds(base + F_MUV * fstr + idn)), make_float2(sigu, sigv),
-                     make_float2(qg_lds(base + F_SIGU * fstr + idn), qg_lds(base + F_SIGV * fstr + idn)), make_float2(rou0, rou2),
-                     p.lambdas, p.epsn, T, gdu, gdv);
+        gd = qg_edge2p<KT>(p.tab, p.K, a, make_float2(muu, muv),
+                           make_float2(qg_lds(base + F_MUU * fstr + idn), qg_lds(base + F_MUV * fstr + idn)), make_float2(sigu, sigv),
+                           make_float2(qg_lds(base + F_SIGU * fstr + idn), qg_lds(base + F_SIGV * fstr + idn)), make_float2(rou0, rou2),
+                           p.lambdas, p.epsn, T);
     }
     // ---- right edge (m,n)->(m,n+1)  (e=2) -----------------------------------------------------------------------
     if (need_right) {
         const long long irt = idx + 1;
         rou1 = qg_lds(base + F_ROU1 * fstr + idx);
         rou3 = qg_lds(base + F_ROU3 * fstr + idx);
-        qg_edge2<KT>(p.tab, p.K, a, make_float2(muu, muv),
-                     make_float2(qg_lds(base + F_MUU * fstr + irt), qg_lds(base + F_MUV * fstr + irt)), make_float2(sigu, sigv),
-                     make_float2(qg_lds(base + F_SIGU * fstr + irt), qg_lds(base + F_SIGV * fstr + irt)), make_float2(rou1, rou3),
-                     p.lambdas, p.epsn, T, gru, grv);
+        gr = qg_edge2p<KT>(p.tab, p.K, a, make_float2(muu, muv),
+                           make_float2(qg_lds(base + F_MUU * fstr + irt), qg_lds(base + F_MUV * fstr + irt)), make_float2(sigu, sigv),
+                           make_float2(qg_lds(base + F_SIGU * fstr + irt), qg_lds(base + F_SIGV * fstr + irt)), make_float2(rou1, rou3),
+                           p.lambdas, p.epsn, T);
     }
     // ---- endpoint-2 exchange (before the node term: the warps of a CTA then never wait for each other again until the
     //      final block reduction, and the cheap halo warp does not stall the barrier) ---------------------------------
     __shared__ float4 sh_dn[TH + 1][QG_TW];
-    sh_dn[r][j] = make_float4(gdu.du2, gdu.do2, gdv.du2, gdv.do2);          // to pixel (m+1,n)
-    const float lf_du_u = __shfl_up_sync(0xffffffffu, gru.du2, 1);             // from pixel (m,n-1)
-    const float lf_do_u = __shfl_up_sync(0xffffffffu, gru.do2, 1);
-    const float lf_du_v = __shfl_up_sync(0xffffffffu, grv.du2, 1);
-    const float lf_do_v = __shfl_up_sync(0xffffffffu, grv.do2, 1);
+    sh_dn[r][j] = make_float4(gd.du2.x, gd.do2.x, gd.du2.y, gd.do2.y);          // to pixel (m+1,n)
+    const float lf_du_u = __shfl_up_sync(0xffffffffu, gr.du2.x, 1);             // from pixel (m,n-1)
+    const float lf_do_u = __shfl_up_sync(0xffffffffu, gr.do2.x, 1);
+    const float lf_du_v = __shfl_up_sync(0xffffffffu, gr.du2.y, 1);
+    const float lf_do_v = __shfl_up_sync(0xffffffffu, gr.do2.y, 1);
     __syncthreads();
+
+    // ---- node term set-up (:87-93).  Full resolution: the bounding box of the K x K sample cloud around the mean,
+    //      |x - mu| <= sqrt2 * sigma * (|s| + |t|) * X_max; inside the image for every belief of the warp -> the clamps of
+    //      :157-162 cannot fire and the warp runs the clamp-free sample loop (relative cell addressing, qg_node_sample_inside).
+    const float pn = is_out ? qg_lds(base + F_PN * fstr + idx) : 0.f;
+    QgSpectral sp;
+    sp.set(pn);
+    bool all_inside = false;
+    if (!SUPER) {
+        bool inside = true;
+        if (is_out) {
+            const int Kq = KT > 0 ? KT : p.K;
+            const float reach = 1.4142135623730951f * p.tab.X[Kq - 1] * (fabsf(sp.s) + fabsf(sp.t)) * 1.0001f;
+            const float ex = fmaf(reach, sigu, 0.01f), ey = fmaf(reach, sigv, 0.01f);
+            inside = (muu - ex >= (float)(-n)) && (muu + ex <= (float)(p.No - 2 - n)) &&
+                     (muv - ey >= (float)(-m)) && (muv + ey <= (float)(p.Mo - 2 - m));
+        }
+        all_inside = __all_sync(0xffffffffu, inside);
+    }
 
     float red[QG_NRED] = {0.f, 0.f, 0.f, 0.f};
     if (is_out) {
         // :37-40 edge part of the assembled gradients: sum_e d1 + shifted d2 (down edge of (m-1,n), right edge of (m,n-1)).
         // Folded into 6 scalars now so that little stays live across the node quadrature.
         const float4 up = sh_dn[r - 1][j];
-        const float E_muu = ((gdu.du1 + gru.du1) + up.x) + lf_du_u;
-        const float E_sigu = ((gdu.do1 + gru.do1) + up.y) + lf_do_u;
-        const float E_muv = ((gdv.du1 + grv.du1) + up.z) + lf_du_v;
-        const float E_sigv = ((gdv.do1 + grv.do1) + up.w) + lf_do_v;
-        const float E_e = (gdu.Ei + gru.Ei) + (gdv.Ei + grv.Ei);                 // :48 edge part
-        const float E_a = (gdu.da + gru.da) + (gdv.da + grv.da);                 // :36 edge part
+        const float E_muu = ((gd.du1.x + gr.du1.x) + up.x) + lf_du_u;
+        const float E_sigu = ((gd.do1.x + gr.do1.x) + up.y) + lf_do_u;
+        const float E_muv = ((gd.du1.y + gr.du1.y) + up.z) + lf_du_v;
+        const float E_sigv = ((gd.do1.y + gr.do1.y) + up.w) + lf_do_v;
+        const float E_e = (gd.Ei.x + gr.Ei.x) + (gd.Ei.y + gr.Ei.y);             // :48 edge part
+        const float E_a = (gd.da.x + gr.da.x) + (gd.da.y + gr.da.y);             // :36 edge part
         float *o = out + (long long)l * pl + idx;
         float *d = DUMP ? p.dbg + (long long)l * pl + idx : nullptr;
         if (DUMP) {
-            d[5 * fstr] = gdu.dp; d[6 * fstr] = gru.dp; d[7 * fstr] = gdv.dp; d[8 * fstr] = grv.dp;
+            d[5 * fstr] = gd.dp.x; d[6 * fstr] = gr.dp.x; d[7 * fstr] = gd.dp.y; d[8 * fstr] = gr.dp.y;
         } else {                                                                 // :45
-            o[F_ROU0 * fstr] = qg_clamp(fmaf(gdu.dp, step, rou0), -p.corr_tor, p.corr_tor);
-            o[F_ROU1 * fstr] = qg_clamp(fmaf(gru.dp, step, rou1), -p.corr_tor, p.corr_tor);
-            o[F_ROU2 * fstr] = qg_clamp(fmaf(gdv.dp, step, rou2), -p.corr_tor, p.corr_tor);
-            o[F_ROU3 * fstr] = qg_clamp(fmaf(grv.dp, step, rou3), -p.corr_tor, p.corr_tor);
+            o[F_ROU0 * fstr] = qg_clamp(fmaf(gd.dp.x, step, rou0), -p.corr_tor, p.corr_tor);
+            o[F_ROU1 * fstr] = qg_clamp(fmaf(gr.dp.x, step, rou1), -p.corr_tor, p.corr_tor);
+            o[F_ROU2 * fstr] = qg_clamp(fmaf(gd.dp.y, step, rou2), -p.corr_tor, p.corr_tor);
+            o[F_ROU3 * fstr] = qg_clamp(fmaf(gr.dp.y, step, rou3), -p.corr_tor, p.corr_tor);
+            if (p.band == 2 && (m == p.pub_row[0] || m == p.pub_row[1])) qg_publish_row(p, it, m, n, l, o, fstr, F_ROU0, 4);
         }
 
-        // ---- node term (:29, :87-116) ---------------------------------------------------------------------------
-        const float pn = qg_lds(base + F_PN * fstr + idx);
-        QgSpectral sp;
-        sp.set(pn);
+        // ---- node quadrature (:29, :94-106) ---------------------------------------------------------------------------
         QgMoments mo;
         if (SUPER) {
             float I1b[16];
@@ -208,11 +245,21 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
             });
         } else {
             const float I1v = __ldg(p.I1 + (long long)m * p.pitchI + n);
-            const int lastx = p.No - 2, lasty = p.Mo - 2;
-            QgTapCache tc;
-            mo = qg_quadrature<KT>(p.tab, p.K, muu, muv, sigu, sigv, sp, -p.lambdad, [&](float2 x) {
-                return qg_node_sample<(KT >= 7)>(p.VV8, p.pitchV, m, n, lastx, lasty, x, I1v, p.epsn, tc);
-            });
+            if (all_inside) {
+                QgTapCacheRel tc;
+                const QgTap8 *vv_mn = p.VV8 + (long long)m * p.pitchV + n;
+                const int koff = -0x4B400000 * (p.pitchV + 1);
+                const long long rowskip = (long long)p.pitchV * (2 * (long long)sizeof(QgTap8));
+                mo = qg_quadrature<KT>(p.tab, p.K, muu, muv, sigu, sigv, sp, -p.lambdad, [&](float2 x) {
+                    return qg_node_sample_inside(vv_mn, p.pitchV, koff, rowskip, x, I1v, p.epsn, tc);
+                });
+            } else {
+                const int lastx = p.No - 2, lasty = p.Mo - 2;
+                QgTapCache tc;
+                mo = qg_quadrature<KT>(p.tab, p.K, muu, muv, sigu, sigv, sp, -p.lambdad, [&](float2 x) {
+                    return qg_node_sample<(KT >= 7)>(p.VV8, p.pitchV, m, n, lastx, lasty, x, I1v, p.epsn, tc);
+                });
+            }
         }
         const QgGrad gn = qg_epilogue(mo, sp, a, sigu, sigv, pn, -3.0f * T);
 
@@ -230,6 +277,10 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
             o[F_SIGU * fstr] = qg_clamp(fmaf(G_sigu, step * p.sig_step, sigu), p.sig_min, p.sig_max);
             o[F_SIGV * fstr] = qg_clamp(fmaf(G_sigv, step * p.sig_step, sigv), p.sig_min, p.sig_max);
             o[F_PN * fstr] = qg_clamp(fmaf(gn.dp, step, pn), -p.corr_tor, p.corr_tor);
+            if (p.band == 2 && (m == p.pub_row[0] || m == p.pub_row[1])) {
+                qg_publish_row(p, it, m, n, l, o, fstr, F_MUU, 5);
+                __threadfence_system();
+            }
         }
     }
 

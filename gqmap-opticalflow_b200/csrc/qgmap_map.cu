@@ -23,7 +23,7 @@ static QgMonParams conv(const QgMonArgs &a)
 {
     QgMonParams q;
     q.I1 = a.I1; q.pitchI = a.pitchI; q.VV = a.VV; q.pitchV = a.pitchV; q.Mo = a.Mo; q.No = a.No; q.M = a.M; q.N = a.N;
-    q.super = a.super; q.lambdad = a.lambdad; q.lambdas = a.lambdas; q.epsn = a.epsn;
+    q.super = a.super; q.lambdad = a.lambdad; q.lambdas = a.lambdas; q.epsn = a.epsn; q.r0 = a.r0; q.r1 = a.r1;
     return q;
 }
 void qgmap_launch_logp(const QgMonArgs &q, const double *uv, double *partials, int nblk, cudaStream_t s)

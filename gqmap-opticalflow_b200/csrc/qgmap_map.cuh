@@ -139,6 +139,7 @@ struct QgMonParams {
     const double *VV; int pitchV;
     int Mo, No, M, N, super;
     double lambdad, lambdas, epsn;
+    int r0, r1;                    // belief rows [r0,r1) this call sums over (a row band's share); whole grid: 0, M
 };
 
 __device__ __forceinline__ double qg_block_sum(double v, double *sh) {
@@ -163,7 +164,7 @@ __global__ void qgmap_logp_kernel(const QgMonParams q, const double *__restrict_
     double acc = 0.0;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < MN; t += (long long)gridDim.x * blockDim.x) {
         const int m = (int)(t % q.M), n = (int)(t / q.M);
-        if (m < 1 || m > q.M - 2 || n < 1 || n > q.N - 2) continue;
+        if (m < 1 || m > q.M - 2 || n < 1 || n > q.N - 2 || m < q.r0 || m >= q.r1) continue;
         const double us = uv[t], vs = uv[t + MN];
         double lp = 0.0;
         if (q.super) {
@@ -197,7 +198,7 @@ __global__ void qgmap_aepe_kernel(const QgMonParams q, const double *__restrict_
     double acc = 0.0;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < MoNo; t += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(t % q.Mo), j = (int)(t / q.Mo);
-        if (i < b || i >= q.Mo - b || j < b || j >= q.No - b) continue;
+        if (i < b || i >= q.Mo - b || j < b || j >= q.No - b || i / sc < q.r0 || i / sc >= q.r1) continue;
         const long long mi = i / sc + (long long)q.M * (j / sc);
         double fu = map[mi], fv = map[mi + MN];
         if (unknown && unknown[t]) { fu = 0.0; fv = 0.0; }

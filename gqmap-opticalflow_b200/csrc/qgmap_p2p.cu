@@ -1,25 +1,22 @@
 // qgmap_p2p.cu -- row bands of ONE frame pair over several GPUs with the halo exchange and the global sums done by our own
-// kernel over NVLink peer memory (BASELINE configs[3]); no NCCL and no host on the per-iteration path.
+// kernels over NVLink peer memory (BASELINE configs[3]); no NCCL and no host on the per-iteration path.
+// Protocol, hazards and the device-side types: qgmap_peer.cuh.
 //
 // Why: the NCCL transport (qgmap_band.cu) needs seven stream operations per iteration (all-reduce, advance kernel, two packs,
-// grouped send/recv, two unpacks) -- ~0.13 ms per iteration at 8 GPUs against 0.58 ms of compute.  Here ONE kernel follows
-// the iteration kernel:
-//   1. every CTA copies a slice of the band's first / last owned row (all 9L planes of the buffer just written) straight
-//      into the neighbour's halo row of the same ping-pong buffer (peer stores, float4);
-//   2. the last CTA to finish stores the band's 4L partial sums into slot [rank] of EVERY rank's mailbox, fences
-//      (system scope) and raises flag[rank] = (step generation, iteration) in every mailbox;
-//   3. it then waits until all flags of its own mailbox carry this iteration, adds the nranks partial sums in rank order
-//      (same bits on every rank, same bits as the single-domain reduction order per band) and advances the control block
-//      (alpha update, anneal, stop test: gqmap_gpu_mixture.m:36,48,50,69-75).
-// Hazards: iteration t reads buffer A and writes B; peers write only halo rows of B during t.  A peer can start t+1 (writing
-// our halo rows of A) only after it has seen OUR flag for t, i.e. after our iteration kernel t has completely finished
-// reading A.  Flags are monotone 64-bit tags, so nothing is ever reset while a peer may still write.
-// A peer that never shows up (crashed rank) must not hang the GPU: the wait gives up after ~10 s, stops the run and
-// sets QgCtrl::comm_error, which qgmap_step_end turns into QGMAP_ERR_COMM.  Every qgmap_step call starts with a ready handshake
-// (qgmap_p2p_ready_kernel) so that set_state on one rank can never race with a faster neighbour's first boundary rows.
+// grouped send/recv, two unpacks) -- ~0.13 ms per iteration at 8 GPUs against 0.58 ms of compute.  Two forms here:
+//   * one thread per belief (qgmap_iter_kernel, qgmap_walk_kernel; QgIterParams::band == 2): the exchange is INSIDE the
+//     iteration kernel -- the threads that update the band's first / last row store them straight into the neighbours' halo
+//     rows (those tiles are scheduled first, so the stores overlap the rest of the band's compute), and the last CTA to retire
+//     posts the partial sums, raises the flags, waits for the other bands and advances the control block (qg_peer_finish).
+//     ONE launch per iteration, captured in the same 25-node CUDA graph as the single-GPU loop.
+//   * four lanes per belief (qgmap_iter_kernel_g4, the super-pixel default): qgmap_p2p_publish_kernel follows the iteration
+//     kernel: all its CTAs copy the boundary rows, its last CTA runs qg_peer_finish -- two launches per iteration.
+// Every qgmap_step call starts with a ready handshake (qgmap_p2p_ready_kernel) so that set_state on one rank can never race
+// with a faster neighbour's first boundary rows.
 #include "qgmap_internal.h"
-#include "qgmap_advance.cuh"
+#include "qgmap_peer.cuh"
 #include <unistd.h>
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -38,25 +35,7 @@
         if (_e != cudaSuccess) QGP_FAIL(h, QGMAP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
 
-#define QG_RANKS_MAX QGMAP_P2P_RANKS_MAX
-
-// One per band handle, in that band's device memory; slot q is written by rank q only.
-struct QgMailbox {
-    double sums[QG_RANKS_MAX][QG_LMAX * QG_NRED];
-    unsigned long long flag[QG_RANKS_MAX];   // (generation << 32 | iteration) rank q has completely published
-    unsigned int ticket;                     // CTAs of the local publish kernel that have finished their copy slice
-};
-
-struct QgP2PParams {
-    QgMailbox *box[QG_RANKS_MAX];            // every rank's mailbox as mapped on this device (own included)
-    float *up[2], *dn[2];                    // neighbours' ping-pong state buffers (null at the image top / bottom)
-    long long up_plane, dn_plane;            // floats per plane in the neighbour's buffers
-    long long up_off, dn_off;                // offset of the halo row we fill inside each of its planes
-    long long first_off, last_off;           // offsets of our first / last owned row inside our planes
-    int rank, nranks, row4, nplanes;         // row4 = float4 per row (P/4), nplanes = 9L
-    unsigned long long gen;                  // generation of this qgmap_step call, already shifted
-    long long timeout_cycles;
-};
+static_assert(QG_RANKS_MAX == QGMAP_P2P_RANKS_MAX, "rank limit of the header and of the mailbox differ");
 
 struct QgP2PBlob {                           // what a rank tells the others (QGMAP_P2P_BLOB_BYTES)
     int magic, pid, device, row_begin, row_end, g0, P, L, N, M;
@@ -68,86 +47,62 @@ static_assert(sizeof(QgP2PBlob) <= QGMAP_P2P_BLOB_BYTES, "blob too large");
 
 struct QgP2P {
     QgMailbox *box = nullptr;                // own mailbox (cudaMalloc)
-    QgP2PParams prm{};
+    QgPeer prm{};                            // host copy
+    QgPeer *d_peer = nullptr;                // device copy read by the kernels (gen is written by the ready kernel)
     std::vector<void *> opened;              // cudaIpcOpenMemHandle mappings to close
     unsigned int gen = 0;
     bool connected = false;
 };
 
-__global__ void __launch_bounds__(256) qgmap_p2p_publish_kernel(const __grid_constant__ QgIterParams p, const __grid_constant__ QgP2PParams q)
+// Tiled iteration kernel only: copy the boundary rows the iteration kernel just wrote into the neighbours' halo rows; the last
+// CTA to finish exchanges the sums and advances the control block.
+__global__ void __launch_bounds__(256) qgmap_p2p_publish_kernel(const __grid_constant__ QgIterParams p, const QgPeer *__restrict__ q)
 {
     QgCtrl *c = p.ctrl;
     if (c->stop) return;
     const int it = c->it, wb = it & 1;                                  // the iteration kernel just wrote buffer wb
     const float *src = p.buf[wb];
-    float *up = q.up[wb], *dn = q.dn[wb];
-    const int total = q.nplanes * q.row4;
+    float *up = q->up[wb], *dn = q->dn[wb];
+    const int row4 = q->row4, total = q->nplanes * row4;
+    const long long up_plane = q->up_plane, dn_plane = q->dn_plane, up_off = q->up_off, dn_off = q->dn_off;
+    const long long first_off = q->first_off, last_off = q->last_off;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int pl = i / q.row4, c4 = i - pl * q.row4;
-        if (up) reinterpret_cast<float4 *>(up + pl * q.up_plane + q.up_off)[c4] =
-                    __ldcg(reinterpret_cast<const float4 *>(src + pl * p.plane + q.first_off) + c4);
-        if (dn) reinterpret_cast<float4 *>(dn + pl * q.dn_plane + q.dn_off)[c4] =
-                    __ldcg(reinterpret_cast<const float4 *>(src + pl * p.plane + q.last_off) + c4);
+        const int pl = i / row4, c4 = i - pl * row4;
+        if (up) reinterpret_cast<float4 *>(up + pl * up_plane + up_off)[c4] =
+                    __ldcg(reinterpret_cast<const float4 *>(src + pl * p.plane + first_off) + c4);
+        if (dn) reinterpret_cast<float4 *>(dn + pl * dn_plane + dn_off)[c4] =
+                    __ldcg(reinterpret_cast<const float4 *>(src + pl * p.plane + last_off) + c4);
     }
     __threadfence_system();
     __syncthreads();
-    __shared__ int sh_last, sh_bad;
-    QgMailbox *mine = q.box[q.rank];
-    if (threadIdx.x == 0) {
-        sh_last = (atomicAdd(&mine->ticket, 1u) == gridDim.x - 1);
-        sh_bad = 0;
-    }
+    __shared__ int sh_last;
+    QgMailbox *mine = q->box[q->rank];
+    if (threadIdx.x == 0) sh_last = (atomicAdd(&mine->ticket, 1u) == gridDim.x - 1);
     __syncthreads();
-    if (!sh_last) return;
-    __threadfence_system();
-    const int ns = p.L * QG_NRED;
-    for (int k = threadIdx.x; k < q.nranks * ns; k += blockDim.x) {
-        const int r = k / ns, j = k - r * ns;
-        q.box[r]->sums[q.rank][j] = c->sums[j];
-    }
-    __threadfence_system();
-    __syncthreads();
-    const unsigned long long tag = q.gen | (unsigned long long)(unsigned int)it;
-    if ((int)threadIdx.x < q.nranks) {
-        *reinterpret_cast<volatile unsigned long long *>(&q.box[threadIdx.x]->flag[q.rank]) = tag;       // publish
-        volatile unsigned long long *f = &mine->flag[threadIdx.x];                                          // wait for rank threadIdx.x
-        const long long t0 = clock64();
-        while (*f < tag) {
-            if (clock64() - t0 > q.timeout_cycles) { sh_bad = 1; break; }
-            __nanosleep(200);
-        }
-    }
-    __syncthreads();
-    __threadfence_system();
-    if (threadIdx.x == 0) {
-        mine->ticket = 0;
-        if (sh_bad) { c->comm_error = 1; c->stop = 1; return; }
-        double tot[QG_LMAX * QG_NRED];
-        for (int k = 0; k < ns; ++k) {
-            double s = 0.0;
-            for (int r = 0; r < q.nranks; ++r) s += *reinterpret_cast<volatile double *>(&mine->sums[r][k]);   // fixed rank order
-            tot[k] = s;
-        }
-        qg_advance(p, c, tot);
-    }
+    if (!sh_last || threadIdx.x >= 32) return;
+    if (threadIdx.x == 0) mine->ticket = 0;
+    __shared__ double sh_mine[QG_LMAX * QG_NRED];
+    for (int k = threadIdx.x; k < p.L * QG_NRED; k += 32) sh_mine[k] = c->sums[k];
+    __syncwarp();
+    qg_peer_finish(p, c, q, sh_mine, threadIdx.x);
 }
 
 // First kernel of every qgmap_step call: "my state buffers are ready to be written into" (stream-ordered after this rank's
 // set_state / previous step), then wait until every peer says the same.  Without it a fast rank could store its first boundary
 // rows into a peer whose set_state has not imported its halo rows yet.  Host-level skew between ranks is allowed to be long.
-__global__ void qgmap_p2p_ready_kernel(const __grid_constant__ QgIterParams p, const __grid_constant__ QgP2PParams q)
+__global__ void qgmap_p2p_ready_kernel(const __grid_constant__ QgIterParams p, QgPeer *q, unsigned long long gen)
 {
     QgCtrl *c = p.ctrl;
     __shared__ int sh_bad;
-    if (threadIdx.x == 0) sh_bad = 0;
+    if (threadIdx.x == 0) { sh_bad = 0; q->gen = gen; }
     __syncthreads();
     __threadfence_system();
-    if ((int)threadIdx.x < q.nranks) {
-        *reinterpret_cast<volatile unsigned long long *>(&q.box[threadIdx.x]->flag[q.rank]) = q.gen;        // tag (gen, iteration 0)
-        volatile unsigned long long *f = &q.box[q.rank]->flag[threadIdx.x];
+    if ((int)threadIdx.x < q->nranks) {
+        *reinterpret_cast<volatile unsigned long long *>(&q->box[threadIdx.x]->flag[q->rank]) = gen;          // tag (gen, iteration 0)
+        volatile unsigned long long *f = &q->box[q->rank]->flag[threadIdx.x];
         const long long t0 = clock64();
-        while (*f < q.gen) {
-            if (clock64() - t0 > 12 * q.timeout_cycles) { sh_bad = 1; break; }
+        while (*f < gen) {
+            if (clock64() - t0 > 12 * q->timeout_cycles) { sh_bad = 1; break; }
             __nanosleep(1000);
         }
     }
@@ -160,6 +115,7 @@ void qgmap_p2p_release(qgmap_handle *h)
     if (!h->p2p) return;
     for (void *m : h->p2p->opened) cudaIpcCloseMemHandle(m);
     if (h->p2p->box) cudaFree(h->p2p->box);
+    if (h->p2p->d_peer) cudaFree(h->p2p->d_peer);
     delete h->p2p;
     h->p2p = nullptr;
 }
@@ -172,6 +128,7 @@ extern "C" int qgmap_band_p2p_export(qgmap_handle *h, void *blob)
     h->p2p = new QgP2P();
     QGP_CUDA(h, cudaMalloc(&h->p2p->box, sizeof(QgMailbox)));
     QGP_CUDA(h, cudaMemset(h->p2p->box, 0, sizeof(QgMailbox)));
+    QGP_CUDA(h, cudaMalloc(&h->p2p->d_peer, sizeof(QgPeer)));
     QgP2PBlob b;
     std::memset(&b, 0, sizeof b);
     b.magic = 0x51503270; b.pid = (int)getpid(); b.device = h->device;
@@ -231,11 +188,12 @@ extern "C" int qgmap_band_p2p_connect(qgmap_handle *h, int rank, int nranks, con
     }
     if (bl[rank].row_begin != h->row_begin || bl[rank].row_end != h->row_end) QGP_FAIL(h, QGMAP_ERR_ARG, "blob %d is not this handle's", rank);
     if (bl[0].row_begin != 0 || bl[nranks - 1].row_end != h->M) QGP_FAIL(h, QGMAP_ERR_ARG, "the bands do not cover the grid");
-    QgP2PParams &q = h->p2p->prm;
+    QgPeer &q = h->p2p->prm;
     std::memset(&q, 0, sizeof q);
     q.rank = rank; q.nranks = nranks; q.row4 = h->P / 4; q.nplanes = F_COUNT * h->L;
     q.first_off = (long long)(h->row_begin - h->g0) * h->P;
     q.last_off = (long long)(h->row_end - 1 - h->g0) * h->P;
+    q.first_row = h->row_begin; q.last_row = h->row_end - 1;
     int clk_khz = 2000000;
     cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, h->device);
     q.timeout_cycles = (long long)clk_khz * 1000LL * 10LL;              // ~10 s
@@ -254,8 +212,14 @@ extern "C" int qgmap_band_p2p_connect(qgmap_handle *h, int rank, int nranks, con
             q.dn_off = (long long)(bl[r].row_begin - 1 - bl[r].g0) * bl[r].P;
         }
     }
+    QGP_CUDA(h, cudaMemcpy(h->p2p->d_peer, &q, sizeof q, cudaMemcpyHostToDevice));
     h->rank = rank; h->nranks = nranks;
-    h->params.band = nranks > 1 ? 1 : 0;
+    // one thread per belief (tiled or row-walking kernel): the iteration kernel carries the exchange itself (band 2); the four-lane
+    // kernel of the super-pixel variant leaves its sums for the publish kernel (band 1)
+    h->params.band = nranks > 1 ? (h->lanes_per_belief == 1 ? 2 : 1) : 0;
+    h->params.peer = h->p2p->d_peer;
+    h->params.pub_row[0] = q.up[0] ? h->row_begin : -1;
+    h->params.pub_row[1] = q.dn[0] ? h->row_end - 1 : -1;
     if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
     h->p2p->connected = true;
     return QGMAP_OK;
@@ -264,17 +228,20 @@ extern "C" int qgmap_band_p2p_connect(qgmap_handle *h, int rank, int nranks, con
 void qgmap_p2p_begin_step(qgmap_handle *h)
 {
     if (!h->p2p || !h->p2p->connected) return;
-    h->p2p->prm.gen = (unsigned long long)(++h->p2p->gen) << 32;
-    qgmap_p2p_ready_kernel<<<1, 32, 0, h->stream>>>(h->params, h->p2p->prm);
+    const unsigned long long gen = (unsigned long long)(++h->p2p->gen) << 32;
+    qgmap_p2p_ready_kernel<<<1, 32, 0, h->stream>>>(h->params, h->p2p->d_peer, gen);
 }
+
+bool qgmap_p2p_fused(const qgmap_handle *h) { return h->p2p && h->p2p->connected && h->params.band == 2; }
 
 int qgmap_p2p_iteration(qgmap_handle *h, long long *launches)
 {
     if (!h->p2p || !h->p2p->connected) QGP_FAIL(h, QGMAP_ERR_COMM, "band handle not connected (qgmap_band_p2p_connect)");
     qgmap_launch_iteration(h);
+    if (h->params.band == 2) return QGMAP_OK;                  // row-walking kernel: the exchange is inside the iteration kernel
     const int total4 = h->p2p->prm.nplanes * h->p2p->prm.row4;
     const int nblk = std::max(1, std::min(32, (total4 + 1023) / 1024));
-    qgmap_p2p_publish_kernel<<<nblk, 256, 0, h->stream>>>(h->params, h->p2p->prm);
+    qgmap_p2p_publish_kernel<<<nblk, 256, 0, h->stream>>>(h->params, h->p2p->d_peer);
     *launches += 1;
     return QGMAP_OK;
 }

@@ -81,3 +81,68 @@ def assemble_bands(dist, state, M):
     for k in mine:
         out[k] = np.asfortranarray(np.concatenate([p[k] for p in parts], axis=0))
     return out
+
+
+def gqmap_gpu_mixture_bands(options, I1, I2, dist, device=None, variant="full", transport=None):
+    """[mu,sigma,alpha,AEPE,Energy,logP] = gqmap_gpu_mixture(options,I1,I2) (gqmap_gpu_mixture.m:1) over the ranks of a
+    torch.distributed job, one row band of the frame pair per rank -- the multi-process twin of options.devices.
+    Every rank passes the same options and frames (host arrays) and calls this collectively.  mu and sigma come back with the rows
+    this rank owns filled in (assemble_bands gathers them); alpha, AEPE, Energy, logP are complete on every rank.
+    The loop is the reference's: iterations up to and including the next monitored one (:52: it == 1 or mod(it,300) == 0), then
+    the monitoring block -- each rank extracts the MAP of its own rows on its GPU and contributes its share of logP and of the AEPE
+    sum; only those two scalars cross ranks (one small all-reduce per monitored iteration)."""
+    import torch
+    from . import host
+    rank, world = dist.get_rank(), dist.get_world_size()
+    its = int(host._opt(options, "its", required=True))
+    every = int(host._opt(options, "log_every", 300))
+    sup = variant == "super"
+    Mo, No = np.asarray(I1).shape
+    M = Mo // 4 if sup else Mo
+    opts = dict(options) if isinstance(options, dict) else {k: getattr(options, k) for k in dir(options) if not k.startswith("_")}
+    rb, re = band_rows(M, rank, world)
+    opts.update(row_begin=rb, row_end=re)
+    s = host.Solver(opts, I1, I2, variant=variant)
+    try:
+        if world > 1:
+            connect_band(s, dist, device=device, transport=transport)
+        init = host._opt(options, "init")
+        if init is not None:
+            s.set_state(init)
+        else:
+            s.init_state(int(host._opt(options, "seed", 0)))
+        tflow = host._opt(options, "trueFlow")
+        if tflow is not None:
+            s.set_truth(tflow, host._opt(options, "unknownIdx"))
+        AEPE = np.full(its, np.nan)
+        Energy = np.zeros(its)
+        logP = np.full(its, np.nan)
+        b = 4 if sup else 1
+        red = torch.zeros(2, dtype=torch.float64, device=device if device is not None else "cpu")
+        it, stopped = 1, False
+        while not stopped and it <= its:
+            nxt = 1 if it == 1 else -(-it // every) * every
+            n = min(nxt, its) - it + 1
+            r = s.step(n, its=its)
+            Energy[it - 1:it - 1 + r["n_done"]] = r["Energy"]
+            it += r["n_done"]
+            stopped = r["stopped"]
+            last = it - 1
+            if r["n_done"] > 0 and (last == 1 or last % every == 0):
+                lp, ae = s.monitor_partial(aepe=tflow is not None)
+                red[0], red[1] = lp, ae
+                if world > 1:
+                    dist.all_reduce(red)
+                logP[last - 1] = float(red[0])
+                if tflow is not None:
+                    AEPE[last - 1] = float(red[1]) / ((Mo - 2 * b) * (No - 2 * b))
+            if r["n_done"] < n:
+                break
+        st = s.get_state()
+    finally:
+        s.close()
+    L = s.L
+    mu = np.stack([st["muu"], st["muv"]], axis=3)
+    sigma = np.stack([st["sigmau"], st["sigmav"]], axis=3)
+    return (np.asfortranarray(mu), np.asfortranarray(sigma), st["alpha"].reshape(1, 1, L), AEPE.reshape(its, 1), Energy.reshape(its, 1),
+            logP.reshape(its, 1))

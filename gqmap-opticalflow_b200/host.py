@@ -61,7 +61,7 @@ def make_config(options, variant):
         v = _opt(options, k)
         if v is not None:
             setattr(cfg, k, float(v))
-    for k in ("alpha_start", "anneal_every", "row_begin", "row_end"):
+    for k in ("alpha_start", "anneal_every", "row_begin", "row_end", "strip_rows"):
         v = _opt(options, k)
         if v is not None:
             setattr(cfg, k, int(v))
@@ -279,6 +279,21 @@ class Solver:
         v = C.c_double(0)
         check(lib.qgmap_aepe(self._h, dptr(uv), dptr(tflow), u8ptr(unk), C.byref(v)), self._h)
         return v.value
+
+    def set_truth(self, tflow, unknown=None):
+        """options.trueFlow / options.unknownIdx for monitor_partial (uploaded once)."""
+        tflow = f64(tflow)
+        if tflow.shape != (self.Mo, self.No, 2):
+            raise ValueError("trueFlow must be Mo x No x 2")
+        unk = None if unknown is None else np.asfortranarray(np.asarray(unknown, dtype=np.uint8))
+        check(lib.qgmap_set_truth(self._h, dptr(tflow), u8ptr(unk)), self._h)
+
+    def monitor_partial(self, aepe=True):
+        """The monitoring block (gqmap_gpu_mixture.m:52-67) for the rows this handle owns, on its device: (share of logP, share of
+        the AEPE numerator).  A row-band run adds the shares of all bands and divides the AEPE sum by (Mo-2b)(No-2b)."""
+        lp, ae = C.c_double(0), C.c_double(0)
+        check(lib.qgmap_monitor_partial(self._h, C.byref(lp), C.byref(ae) if aepe else None), self._h)
+        return lp.value, ae.value
 
     def debug_gradients(self):
         names = ("G_muu", "G_muv", "G_sigu", "G_sigv", "dpn", "drou", "e_px", "da_px")

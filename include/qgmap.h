@@ -69,6 +69,7 @@ typedef struct {
     int32_t row_begin, row_end;     /* rows [row_begin,row_end) of the belief grid owned by this handle
                                        (row-band decomposition); 0,0 = whole grid                          */
     int32_t log_every;              /* monitoring cadence of qgmap_solve: 300 (:52)                        */
+    int32_t strip_rows;             /* full-resolution kernel: rows one warp walks; 0 = chosen from the grid size */
 } qgmap_config;
 
 typedef struct qgmap_handle qgmap_handle;
@@ -123,6 +124,12 @@ int qgmap_logp(qgmap_handle *h, const double *map, double *lp);
 /* AEPE of a map against ground truth, gqmap_gpu_mixture.m:63-64 / gqmap_gpuSuper_mix_entropy.m:58-63.
  * map M x N x 2 (belief grid), tflow Mo x No x 2, unknown Mo x No uint8 (may be NULL). */
 int qgmap_aepe(qgmap_handle *h, const double *map, const double *tflow, const uint8_t *unknown, double *aepe);
+/* The same monitoring block for the rows a handle OWNS (row bands; gqmap_gpu_mixture.m:52-67), computed where the rows live:
+ * qgmap_set_truth uploads options.trueFlow / options.unknownIdx once; qgmap_monitor_partial extracts the MAP of the handle's
+ * stored rows on its device and returns its share of profile_logP (:148-154) and of the AEPE numerator (:63-64; divide the sum of
+ * all shares by (Mo-2b)(No-2b), b = 1, or 4 for the super-pixel variant).  Either output may be NULL. */
+int qgmap_set_truth(qgmap_handle *h, const double *tflow, const uint8_t *unknown);
+int qgmap_monitor_partial(qgmap_handle *h, double *logp_share, double *aepe_sum_share);
 
 /* One-call solver == [mu,sigma,alpha,AEPE,Energy,logP] = gqmap_gpu_mixture(options,I1,I2)
  * (gqmap_gpu_mixture.m:1) or gqmap_gpuSuper_mix_entropy (same signature), all host buffers.

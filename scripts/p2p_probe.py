@@ -3,7 +3,7 @@ import importlib, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
-os.environ["QGMAP_GROUP_TRANSPORT"] = sys.argv[1] if len(sys.argv) > 1 else "p2p"
+os.environ["QGMAP_GROUP_TRANSPORT"] = sys.argv[1] if len(sys.argv) > 1 else "p2p-shared"
 pkg = importlib.import_module("gqmap-opticalflow_b200")
 from oracle import oracle as O
 from conftest import make_problem, options_from_cfg, state_dict

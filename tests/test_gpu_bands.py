@@ -77,3 +77,35 @@ def test_solve_with_options_devices_matches_single_domain(pkg, O, variant, tmp_p
     assert sorted(p.name for p in (tmp_path / "b").iterdir()) == ["1.png", "12.png", "4.png", "8.png"]
     for p in (tmp_path / "a").iterdir():
         assert p.read_bytes() == (tmp_path / "b" / p.name).read_bytes()
+
+
+@pytest.mark.parametrize("variant,shape,L,K,T,nbands,form", [
+    ("full", (61, 70), 2, 3, 0.0, 2, "tile"), ("full", (96, 45), 3, 5, 0.2, 3, "tile"), ("full", (96, 45), 3, 5, 0.2, 3, "walk"),
+    ("super", (128, 96), 3, 5, 0.2, 2, "tile"),
+])
+def test_peer_memory_transport_on_one_gpu(pkg, O, monkeypatch, variant, shape, L, K, T, nbands, form):
+    """The peer-memory exchange (csrc/qgmap_peer.cuh: boundary rows stored into the neighbour's halo rows, sums and flags through
+    the mailboxes, waits inside the kernels) on a 1-GPU box: the bands' streams run concurrently on the same device
+    (QGMAP_GROUP_TRANSPORT=p2p-shared, a test-only switch).  One lane per belief = the exchange fused into the iteration kernel
+    (tiled and row-walking form), CUDA-graph launches included (30 iterations > one 25-node graph); four lanes per belief =
+    iteration kernel + publish kernel.  Same bits as the single domain, across two step calls (generation tags)."""
+    monkeypatch.setenv("QGMAP_GROUP_TRANSPORT", "p2p-shared")
+    monkeypatch.setenv("QGMAP_ITER", form)
+    sup = variant == "super"
+    Mo, No = shape
+    cfg, I1, I2, st = make_problem(O, Mo, No, L, K, super=sup, seed=5, T=T, small_sigma=True)
+    opts = options_from_cfg(cfg, T=T, alpha_scale=1e-5)
+    with pkg.Solver(opts, I1, I2, variant=variant) as s:
+        s.set_state(state_dict(st), T=T, it=495)
+        r1 = s.step(36)
+        a = s.get_state()
+    with pkg.BandGroup(opts, I1, I2, nbands, variant=variant) as g:
+        g.set_state(state_dict(st), T=T, it=495)
+        ra = g.step(6)
+        rb = g.step(30)
+        b = g.get_state()
+    assert ra["n_done"] == 6 and rb["n_done"] == 30
+    for f in ("muu", "muv", "sigmau", "sigmav", "pn", "rou"):
+        assert np.array_equal(a[f], b[f]), f
+    E = np.concatenate([ra["Energy"], rb["Energy"]])
+    assert np.abs(E / r1["Energy"] - 1).max() < 1e-12 and np.abs(a["alpha"] - b["alpha"]).max() < 1e-14
