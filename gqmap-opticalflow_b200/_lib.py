@@ -63,6 +63,7 @@ SIGNATURES = {
     "qgmap_get_map": (C.c_int, [C.c_void_p, _DP]),
     "qgmap_logp": (C.c_int, [C.c_void_p, _DP, _DP]),
     "qgmap_aepe": (C.c_int, [C.c_void_p, _DP, _DP, _U8P, _DP]),
+    "qgmap_image_dims": (C.c_int, [C.c_void_p, _IP, _IP]),
     "qgmap_set_truth": (C.c_int, [C.c_void_p, _DP, _U8P]),
     "qgmap_monitor_partial": (C.c_int, [C.c_void_p, _DP, _DP]),
     "qgmap_solve": (C.c_int, [C.POINTER(QgmapConfig), _DP, _DP, C.c_int, C.c_int, C.c_int, C.POINTER(_DP), C.c_uint64,

@@ -119,7 +119,7 @@ static void free_handle(qgmap_handle *h)
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->evb0) cudaEventDestroy(h->evb0);
     if (h->evb1) cudaEventDestroy(h->evb1);
-    void *ptrs[] = {h->I1f, h->VVf, h->I1d, h->VVd, h->buf[0], h->buf[1], h->dbg, h->ctrl, h->partials, h->gpartials, h->tickets, h->hist[0],
+    void *ptrs[] = {h->I1f, h->VVf, h->VVh, h->I1d, h->VVd, h->buf[0], h->buf[1], h->dbg, h->ctrl, h->partials, h->gpartials, h->tickets, h->hist[0],
                     h->hist[1], h->hist[2], h->stage, h->mon_partials, h->d_map, h->d_tflow, h->d_unknown};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (h->ctrl_host) cudaFreeHost(h->ctrl_host);
@@ -176,6 +176,7 @@ int qgmap_pick_strip_rows(int strips_x, int out_rows, int L, int sms, int K, int
 
 extern "C" int qgmap_create(const qgmap_config *cfg, const double *I1, const double *I2, int Mo, int No, qgmap_handle **out)
 {
+    return qg_guard([&]() -> int {
     if (!cfg || !I1 || !I2 || !out) QG_FAIL((qgmap_handle *)nullptr, QGMAP_ERR_ARG, "qgmap_create: NULL argument");
     *out = nullptr;
     if (cfg->struct_size != (int32_t)sizeof(qgmap_config))
@@ -243,6 +244,22 @@ extern "C" int qgmap_create(const qgmap_config *cfg, const double *I1, const dou
         qgmap_pack8_kernel<<<dim3((h->pitch4 + 127) / 128, Mo + 2), 128, 0, h->stream>>>(h->VVd, h->pitchV, Mo + 2, No + 2,
                                                                                       reinterpret_cast<float4 *>(h->VVf), h->pitch4, Mo + 2);
         QG_CUDA_C(cudaGetLastError());
+        // fp16 4x4-block gather layout for wide beliefs -- kept only if the padded frame is exactly representable (integer grey
+        // levels, as the reference's double(rgb2gray(...)) frames are); QGMAP_TAPS=f32 disables it (A/B measurements)
+        const char *tenv = getenv("QGMAP_TAPS");
+        if (!sup && !(tenv && !strcmp(tenv, "f32"))) {
+            int *d_flag = nullptr, flag = 0;
+            QG_CUDA_C(cudaMalloc(&h->VVh, (size_t)(Mo + 2) * h->pitch4 * sizeof(QgTap16h)));
+            QG_CUDA_C(cudaMalloc(&d_flag, sizeof(int)));
+            QG_CUDA_C(cudaMemsetAsync(d_flag, 0, sizeof(int), h->stream));
+            qgmap_pack16h_kernel<<<dim3((h->pitch4 + 127) / 128, Mo + 2), 128, 0, h->stream>>>(h->VVd, h->pitchV, Mo + 2, No + 2,
+                                                                                            reinterpret_cast<uint4 *>(h->VVh), h->pitch4, Mo + 2, d_flag);
+            QG_CUDA_C(cudaGetLastError());
+            QG_CUDA_C(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            QG_CUDA_C(cudaStreamSynchronize(h->stream));
+            cudaFree(d_flag);
+            if (flag) { cudaFree(h->VVh); h->VVh = nullptr; }
+        }
     }
 
     // tiles.  One thread per (belief pixel, component) when that fills the GPU; four lanes per belief (edge quadratures and
@@ -296,7 +313,7 @@ extern "C" int qgmap_create(const qgmap_config *cfg, const double *I1, const dou
         p.tab.X[k] = (float)X[k]; p.tab.W[k] = (float)W[k];
         p.tab.WX[k] = (float)(W[k] * X[k]); p.tab.WXX[k] = (float)(W[k] * X[k] * X[k]);
     }
-    p.I1 = h->I1f; p.pitchI = h->pitchI; p.VV8 = h->VVf; p.pitchV = h->pitch4;
+    p.I1 = h->I1f; p.pitchI = h->pitchI; p.VV8 = h->VVf; p.VVh = h->VVh; p.pitchV = h->pitch4;
     p.buf[0] = h->buf[0]; p.buf[1] = h->buf[1];
     p.plane = h->plane; p.P = h->P; p.M = M; p.N = N; p.L = h->L; p.Mo = Mo; p.No = No;
     p.g0 = h->g0; p.out_r0 = h->out_r0; p.out_r1 = h->out_r1; p.K = h->K; p.band = 0;
@@ -306,6 +323,7 @@ extern "C" int qgmap_create(const qgmap_config *cfg, const double *I1, const dou
     p.step0 = cfg->step0; p.step_tau = cfg->step_tau; p.alpha_scale = cfg->alpha_scale; p.drate = cfg->drate;
     p.sig_step = (float)cfg->sigma_step_scale; p.T_floor = cfg->T_floor; p.tor = cfg->tor; p.alpha_start = cfg->alpha_start; p.alpha_mode = cfg->alpha_mode;
     p.anneal_every = cfg->anneal_every;
+    { const char *nenv = getenv("QGMAP_NARROW"); p.narrow_path = !(nenv && !strcmp(nenv, "0")); }
     p.ctrl = h->ctrl; p.partials = h->partials; p.gpartials = h->gpartials; p.tickets = h->tickets; p.strip_rows = strip_rows;
     QG_CUDA_C(cudaStreamSynchronize(h->stream));
     if (ensure_hist(h, 1024) != QGMAP_OK) { free_handle(h); return QGMAP_ERR_CUDA; }
@@ -313,6 +331,7 @@ extern "C" int qgmap_create(const qgmap_config *cfg, const double *I1, const dou
 #undef QG_CUDA_C
     *out = h;
     return QGMAP_OK;
+    });
 }
 
 extern "C" int qgmap_destroy(qgmap_handle *h)
@@ -328,6 +347,14 @@ extern "C" int qgmap_dims(const qgmap_handle *h, int *M, int *N, int *L)
     if (M) *M = h->M;
     if (N) *N = h->N;
     if (L) *L = h->L;
+    return QGMAP_OK;
+}
+
+extern "C" int qgmap_image_dims(const qgmap_handle *h, int *Mo, int *No)
+{
+    if (!h) return QGMAP_ERR_ARG;
+    if (Mo) *Mo = h->Mo;
+    if (No) *No = h->No;
     return QGMAP_OK;
 }
 
@@ -454,6 +481,7 @@ void qgmap_random_state(const qgmap_config &c, size_t n, int L, uint64_t seed, s
 
 extern "C" int qgmap_init_state(qgmap_handle *h, uint64_t seed)
 {
+    return qg_guard([&]() -> int {
     if (!h) return QGMAP_ERR_ARG;
     const size_t n = (size_t)h->M * h->N * h->L;
     const qgmap_config &c = h->cfg;
@@ -461,6 +489,7 @@ extern "C" int qgmap_init_state(qgmap_handle *h, uint64_t seed)
     qgmap_random_state(c, n, h->L, seed, w, muu, muv, sigu, sigv);
     return qgmap_set_state(h, muu.data(), muv.data(), sigu.data(), sigv.data(), pn.data(), rou.data(), w.data(), nullptr,
                            c.temperature, 1);
+    });
 }
 
 static const int kGraphLen = 25;
@@ -486,8 +515,11 @@ int qgmap_prepare_step(qgmap_handle *h, int n, int its)
     if (!h->has_state) QG_FAIL(h, QGMAP_ERR_STATE, "qgmap_step before qgmap_set_state/qgmap_init_state");
     if (h->pending) QG_FAIL(h, QGMAP_ERR_STATE, "qgmap_step_begin: previous step not ended");
     QG_CUDA(h, cudaSetDevice(h->device));
-    // history is indexed by iteration: room for what can actually run now (its may be "unbounded")
-    int rc = ensure_hist(h, (int)std::min<long long>((long long)its, (long long)h->ctrl_host->it - 1 + n));
+    // history is indexed by iteration: room for what can actually run now (its may be "unbounded").  A state resumed PAST its
+    // (set_state(it > its)) still executes one iteration before the reference's `it > its` test fires (:74-75), so the bound
+    // is max(its, it0), not its.
+    const long long it0 = h->ctrl_host->it;
+    int rc = ensure_hist(h, (int)std::min<long long>(std::max<long long>((long long)its, it0), it0 - 1 + std::max(n, 1)));
     if (rc) return rc;
     h->it0 = h->ctrl_host->it;
     h->band_steps_enqueued = 0;
@@ -834,6 +866,7 @@ extern "C" int qgmap_monitor_partial(qgmap_handle *h, double *logp_share, double
 extern "C" int qgmap_debug_gradients(qgmap_handle *h, double *G_muu, double *G_muv, double *G_sigu, double *G_sigv,
                                      double *dpn, double *drou, double *e_px, double *da_px)
 {
+    return qg_guard([&]() -> int {
     if (!h) return QGMAP_ERR_ARG;
     if (!h->has_state) QG_FAIL(h, QGMAP_ERR_STATE, "qgmap_debug_gradients: no state set");
     QG_CUDA(h, cudaSetDevice(h->device));
@@ -859,6 +892,7 @@ extern "C" int qgmap_debug_gradients(qgmap_handle *h, double *G_muu, double *G_m
         QG_CUDA(h, cudaStreamSynchronize(h->stream));
     }
     return QGMAP_OK;
+    });
 }
 
 // ---- stateless get_map_mex replacement ---------------------------------------------------------------------------------
@@ -893,8 +927,10 @@ extern "C" int qgmap_find_map(const double *alpha, const double *mu_u, const dou
 static thread_local std::string g_dump_dir;
 extern "C" int qgmap_solve_set_dump_dir(const char *dir)
 {
+    return qg_guard([&]() -> int {
     g_dump_dir = dir ? dir : "";
     return QGMAP_OK;
+    });
 }
 static int dump_map_png(qgmap_handle *h, int it)
 {
@@ -925,6 +961,7 @@ extern "C" int qgmap_solve(const qgmap_config *cfg, const double *I1, const doub
                            double *mu, double *sigma, double *alpha, double *AEPE, double *Energy, double *logP,
                            int *its_done)
 {
+    return qg_guard([&]() -> int {
     qgmap_handle *nh = nullptr;
     if (its < 1) QG_FAIL(nh, QGMAP_ERR_ARG, "qgmap_solve: its=%d", its);
     qgmap_handle *h = nullptr;
@@ -974,6 +1011,7 @@ extern "C" int qgmap_solve(const qgmap_config *cfg, const double *I1, const doub
     g_solve_launches = launches; g_solve_ms = ms;
     qgmap_destroy(h);
     return QGMAP_OK;
+    });
 }
 
 // gqmap_gpu_mixture(options,I1,I2) with options.devices: the loop of qgmap_solve over a band group
@@ -983,6 +1021,7 @@ extern "C" int qgmap_group_solve(const qgmap_config *cfg, const double *I1, cons
                                  double *mu, double *sigma, double *alpha, double *AEPE, double *Energy, double *logP,
                                  int *its_done)
 {
+    return qg_guard([&]() -> int {
     qgmap_handle *nh = nullptr;
     if (its < 1 || nbands < 1) QG_FAIL(nh, QGMAP_ERR_ARG, "qgmap_group_solve: its=%d nbands=%d", its, nbands);
     qgmap_group *g = nullptr;
@@ -1058,6 +1097,7 @@ extern "C" int qgmap_group_solve(const qgmap_config *cfg, const double *I1, cons
     g_solve_launches = 0; g_solve_ms = ms;
     qgmap_group_destroy(g);
     return QGMAP_OK;
+    });
 }
 
 void qgmap_launch_iteration(const qgmap_handle *h) { launch_iter(h, false); }

@@ -93,6 +93,7 @@ int qgmap_band_refresh(qgmap_handle *h) { (void)h; return QGMAP_OK; }   // set_s
 
 extern "C" int qgmap_band_unique_id(void *id128)
 {
+    return qg_guard([&]() -> int {
     qgmap_handle *nh = nullptr;
     if (!id128) return QGMAP_ERR_ARG;
     std::string why;
@@ -102,10 +103,12 @@ extern "C" int qgmap_band_unique_id(void *id128)
     QGB_NCCL(nh, g_nccl.GetUniqueId(&id));
     std::memcpy(id128, &id, sizeof id);
     return QGMAP_OK;
+    });
 }
 
 extern "C" int qgmap_band_connect(qgmap_handle *h, int rank, int nranks, const void *id128)
 {
+    return qg_guard([&]() -> int {
     if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return QGMAP_ERR_ARG;
     if (h->in_group) QGB_FAIL(h, QGMAP_ERR_STATE, "handle belongs to a qgmap_group");
     std::string why;
@@ -123,6 +126,7 @@ extern "C" int qgmap_band_connect(qgmap_handle *h, int rank, int nranks, const v
     h->params.band = nranks > 1 ? 1 : 0;
     if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
     return QGMAP_OK;
+    });
 }
 
 // row `grow` (global index) of all 9L planes of state buffer b  <->  contiguous [9L][N]
@@ -210,6 +214,7 @@ extern "C" int qgmap_group_destroy(qgmap_group *g)
 extern "C" int qgmap_group_create(const qgmap_config *cfg, const double *I1, const double *I2, int Mo, int No, int nbands,
                                   const int *devices, qgmap_group **out)
 {
+    return qg_guard([&]() -> int {
     qgmap_handle *nh = nullptr;
     if (!cfg || !I1 || !I2 || !out || nbands < 1) QGB_FAIL(nh, QGMAP_ERR_ARG, "qgmap_group_create: bad argument");
     *out = nullptr;
@@ -273,6 +278,7 @@ extern "C" int qgmap_group_create(const qgmap_config *cfg, const double *I1, con
     if (cudaEventCreate(&g->ev0) != cudaSuccess || cudaEventCreate(&g->ev1) != cudaSuccess) return bail(QGMAP_ERR_CUDA);
     *out = g;
     return QGMAP_OK;
+    });
 }
 
 extern "C" int qgmap_group_dims(const qgmap_group *g, int *M, int *N, int *L, int *nbands)
@@ -298,6 +304,7 @@ extern "C" int qgmap_group_set_state(qgmap_group *g, const double *muu, const do
 
 extern "C" int qgmap_group_init_state(qgmap_group *g, uint64_t seed)
 {
+    return qg_guard([&]() -> int {
     if (!g) return QGMAP_ERR_ARG;
     qgmap_handle *h0 = g->bands[0];              // the full-grid arrays are drawn once; every band keeps its rows
     const size_t n = (size_t)g->M * g->N * g->L;
@@ -305,6 +312,7 @@ extern "C" int qgmap_group_init_state(qgmap_group *g, uint64_t seed)
     qgmap_random_state(h0->cfg, n, g->L, seed, w, muu, muv, sigu, sigv);
     return qgmap_group_set_state(g, muu.data(), muv.data(), sigu.data(), sigv.data(), pn.data(), rou.data(), w.data(), nullptr,
                                  h0->cfg.temperature, 1);
+    });
 }
 
 extern "C" int qgmap_group_get_state(qgmap_group *g, double *muu, double *muv, double *sigu, double *sigv, double *pn, double *rou,

@@ -10,6 +10,7 @@
 //   * 1-p^2 is formed as (1-p)(1+p) and sqrt(1-p^2) as sqrt(1-p)*sqrt(1+p).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #define QG_LMAX 10
@@ -115,6 +116,8 @@ struct QgCtrl {
 
 struct QgIterParams {
     const float *I1;  int pitchI;      // Mo x No row-major
+    const struct QgTap16h *VVh;        // the same frame as 4 x 4 blocks of fp16 (one sector per sample) -- only when every value of
+                                       // the padded frame is exactly representable in fp16 (integer grey levels); else null
     const QgTap8 *VV8; int pitchV;     // padded second frame (getVV), packed for the gather: VV8[y*pitchV + x] holds
                                        // VV(y, x..x+3) and VV(y+1, x..x+3) in one 32-byte sector, so the 16 taps of a bicubic
                                        // sample are TWO 256-bit loads (LDG.E.256), each lane touching exactly one sector
@@ -138,6 +141,7 @@ struct QgIterParams {
     double *gpartials;                 // row-walking kernel: [strip rows x L][QG_NRED], second reduction level
     unsigned int *tickets;             // row-walking kernel: [strip rows x L] finished-strip counters
     int strip_rows;                    // row-walking kernel: rows one warp walks
+    int narrow_path;                   // 1: warps of narrow beliefs use the 5x5 tap window (QGMAP_NARROW=0 disables: A/B, tests)
     int pub_row[2];                    // band == 2: global row whose updated beliefs also go to the band above [0] / below [1]; -1 = none
     const struct QgPeer *peer;         // band == 2: peer-memory exchange fused into the row-walking kernel (qgmap_peer.cuh)
     double *hist_energy, *hist_dmu, *hist_dsig;   // its entries each, index it-1
@@ -676,6 +680,98 @@ __device__ __forceinline__ float qg_node_sample_inside(const QgTap8 *__restrict_
     h01 = qg_fma2(tc.v01.p[1], qg_bc(w1.x), h01);  h23 = qg_fma2(tc.v23.p[1], qg_bc(w1.x), h23);
     h01 = qg_fma2(tc.v01.p[2], qg_bc(w2.x), h01);  h23 = qg_fma2(tc.v23.p[2], qg_bc(w2.x), h23);
     h01 = qg_fma2(tc.v01.p[3], qg_bc(-n3.x), h01); h23 = qg_fma2(tc.v23.p[3], qg_bc(-n3.x), h23);
+    const float v = fmaf(h23.y, -n3.y, fmaf(h23.x, w2.y, fmaf(h01.y, w1.y, h01.x * -n0.y)));
+    const float d = fmaf(-0.25f, v, I1v);
+    return qg_sqrt(fmaf(d, d, epsn));
+}
+
+// ---- narrow beliefs: the whole K x K sample cloud fits into a 2 x 2 block of cells ---------------------------------------
+// Once a belief has converged (sigma ~ 0.07 px) its samples spread over a fraction of a pixel, but they still straddle a cell
+// boundary for most beliefs, so the tap cache reloads a few times per quadrature row -- each reload a dependent L1 round trip on
+// the warp's critical path (ncu: 62% of the long-scoreboard samples of the K=5 kernel sit on the first use of freshly loaded taps).
+// Here the 5 x 5 taps that cover the 2 x 2 cells are loaded ONCE per belief; a sample in the cell right of / below the window origin
+// uses the same registers with its four weights shifted by one position (a fifth weight of exactly 0 joins at the free end).
+// The products with the zero weight are exact zeros and the remaining operations are those of qg_node_sample in the same order,
+// so the value is bit-identical.  No loads, no branches, no address arithmetic inside the quadrature loop.
+struct QgWin5 {
+    float2 r01[5], r23[5];      // window rows (0,1) and (2,3), interleaved by row inside each column like QgTap8
+    float r4[5];                // window row 4
+    int kx0, ky0;               // magic-number floor bits of the window origin cell (relative to the belief's pixel)
+};
+__device__ __forceinline__ float2 qg_ld64(const void *ptr) {
+    float2 v;
+    asm("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(ptr));
+    return v;
+}
+// lo = (x,y) of the cloud's lower corner relative to the pixel; vv_mn = &VV8[m*pitchV + n]
+__device__ __forceinline__ void qg_win5_load(QgWin5 &w, const QgTap8 *__restrict__ vv_mn, int pitchV, float2 lo)
+{
+    const float2 t = qg_add2_rm(lo, qg_bc(12582912.0f));
+    w.kx0 = __float_as_int(t.x); w.ky0 = __float_as_int(t.y);
+    const QgTap8 *e = vv_mn + ((w.ky0 - 0x4B400000) * pitchV + (w.kx0 - 0x4B400000));
+    const QgTap8 a = qg_ld256(e), c = qg_ld256(e + 2 * pitchV), g = qg_ld256(e + 4 * pitchV);
+    const float2 b = qg_ld64(e + 4), d = qg_ld64(e + 2 * pitchV + 4), h = qg_ld64(e + 4 * pitchV + 4);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { w.r01[k] = a.p[k]; w.r23[k] = c.p[k]; w.r4[k] = g.p[k].x; }
+    w.r01[4] = b; w.r23[4] = d; w.r4[4] = h.x;
+}
+__device__ __forceinline__ float qg_node_sample_win5(const QgWin5 &w, float2 x, float I1v, float epsn)
+{
+    const float2 magic = qg_bc(12582912.0f);
+    const float2 t = qg_add2_rm(x, magic);
+    const float2 fr = qg_sub2(x, qg_sub2(t, magic));
+    const bool dx = __float_as_int(t.x) != w.kx0, dy = __float_as_int(t.y) != w.ky0;     // sample in the second cell of the axis
+    float2 n0, w1, w2, n3;
+    qg_cubic_w2(fr, n0, w1, w2, n3);
+    const float a0 = -n0.x, a1 = w1.x, a2 = w2.x, a3 = -n3.x, b0 = -n0.y, b1 = w1.y, b2 = w2.y, b3 = -n3.y;
+    const float wx0 = dx ? 0.0f : a0, wx1 = dx ? a0 : a1, wx2 = dx ? a1 : a2, wx3 = dx ? a2 : a3, wx4 = dx ? a3 : 0.0f;
+    const float wy0 = dy ? 0.0f : b0, wy1 = dy ? b0 : b1, wy2 = dy ? b1 : b2, wy3 = dy ? b2 : b3, wy4 = dy ? b3 : 0.0f;
+    float2 h01 = qg_mul2(w.r01[0], qg_bc(wx0)), h23 = qg_mul2(w.r23[0], qg_bc(wx0));
+    float h4 = w.r4[0] * wx0;
+    h01 = qg_fma2(w.r01[1], qg_bc(wx1), h01); h23 = qg_fma2(w.r23[1], qg_bc(wx1), h23); h4 = fmaf(w.r4[1], wx1, h4);
+    h01 = qg_fma2(w.r01[2], qg_bc(wx2), h01); h23 = qg_fma2(w.r23[2], qg_bc(wx2), h23); h4 = fmaf(w.r4[2], wx2, h4);
+    h01 = qg_fma2(w.r01[3], qg_bc(wx3), h01); h23 = qg_fma2(w.r23[3], qg_bc(wx3), h23); h4 = fmaf(w.r4[3], wx3, h4);
+    h01 = qg_fma2(w.r01[4], qg_bc(wx4), h01); h23 = qg_fma2(w.r23[4], qg_bc(wx4), h23); h4 = fmaf(w.r4[4], wx4, h4);
+    const float v = fmaf(h4, wy4, fmaf(h23.y, wy3, fmaf(h23.x, wy2, fmaf(h01.y, wy1, h01.x * wy0))));
+    const float d = fmaf(-0.25f, v, I1v);
+    return qg_sqrt(fmaf(d, d, epsn));
+}
+
+// ---- wide beliefs: one sector per sample ----------------------------------------------------------------------------------
+// While the beliefs are wide (the first thousands of iterations; for ever on frames whose mixture never settles) every sample of
+// every lane lands in its own cell and the kernel is bound by the L1 data stage, not by arithmetic: a warp-wide gather of
+// scattered 32-byte sectors retires about one sector per clock, and the 16 fp32 taps of a sample are two sectors
+// (ncu, 4K, L=3, K=5: l1tex data-stage 84% busy, 64 sector wavefronts per warp-sample = the whole 4.2 ms).
+// The reference's frames are grey levels -- double(rgb2gray(...)), optical_flow.m:8-11: integers 0..255 -- and getVV's quadratic
+// border extrapolation 3a-3b+c (:198-207) keeps them integers below 2048, which fp16 holds EXACTLY.  For such frames the 4 x 4 tap
+// block of cell (y,x) is stored as one 32-byte entry of fp16 values: ONE 256-bit load, one sector per sample and lane, and the
+// values converted back to fp32 are bit-identical to the fp32 layout's.  Entry layout: word c (c = 0..3) = rows (y, y+1) of column
+// x+c, word 4+c = rows (y+2, y+3): converted pairwise they are the float2 operands of the row-pair FFMA2 stream of qg_node_sample.
+struct __align__(32) QgTap16h { unsigned int w[8]; };
+__device__ __forceinline__ QgTap16h qg_ld256h(const QgTap16h *ptr) {
+    QgTap16h v;
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]), "=r"(v.w[4]), "=r"(v.w[5]), "=r"(v.w[6]), "=r"(v.w[7]) : "l"(ptr));
+    return v;
+}
+__device__ __forceinline__ float2 qg_h2f2(unsigned int w) {
+    return __half22float2(*reinterpret_cast<const __half2 *>(&w));
+}
+// vh_mn = &VVh[m*pitchV + n]; no tap cache (a wide belief changes cell with every sample): the load is unconditional, so the
+// compiler is free to issue the loads of the next samples of the unrolled row ahead of the arithmetic of this one.
+__device__ __forceinline__ float qg_node_sample_wide(const QgTap16h *__restrict__ vh_mn, int pitchV, int koff, float2 x, float I1v, float epsn)
+{
+    const float2 magic = qg_bc(12582912.0f);
+    const float2 t = qg_add2_rm(x, magic);
+    const float2 fr = qg_sub2(x, qg_sub2(t, magic));
+    const QgTap16h e = qg_ld256h(vh_mn + (__float_as_int(t.y) * pitchV + __float_as_int(t.x) + koff));
+    float2 n0, w1, w2, n3;
+    qg_cubic_w2(fr, n0, w1, w2, n3);
+    float2 h01 = qg_mul2(qg_h2f2(e.w[0]), qg_bc(-n0.x));
+    float2 h23 = qg_mul2(qg_h2f2(e.w[4]), qg_bc(-n0.x));
+    h01 = qg_fma2(qg_h2f2(e.w[1]), qg_bc(w1.x), h01);  h23 = qg_fma2(qg_h2f2(e.w[5]), qg_bc(w1.x), h23);
+    h01 = qg_fma2(qg_h2f2(e.w[2]), qg_bc(w2.x), h01);  h23 = qg_fma2(qg_h2f2(e.w[6]), qg_bc(w2.x), h23);
+    h01 = qg_fma2(qg_h2f2(e.w[3]), qg_bc(-n3.x), h01); h23 = qg_fma2(qg_h2f2(e.w[7]), qg_bc(-n3.x), h23);
     const float v = fmaf(h23.y, -n3.y, fmaf(h23.x, w2.y, fmaf(h01.y, w1.y, h01.x * -n0.y)));
     const float d = fmaf(-0.25f, v, I1v);
     return qg_sqrt(fmaf(d, d, epsn));

@@ -1,6 +1,7 @@
 // qgmap_host.cpp -- host-side pieces of libqgmap.so that need no GPU: Gauss-Hermite tables, projsplx,
 // flowToColor_mex replacement, status strings.
 #include "../../include/qgmap.h"
+#include "qgmap_guard.h"
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -104,6 +105,7 @@ static void colorwheel(double cw[55][3])
 extern "C" int qgmap_flow_to_color(const double *flow, int M, int N, double max_flow,
                                    uint8_t *img, double *flo, double *stats, uint8_t *unknown)
 {
+    return qg_guard([&]() -> int {
     if (!flow || M < 1 || N < 1) return QGMAP_ERR_ARG;
     const size_t MN = (size_t)M * N;
     const double UNKNOWN_FLOW_THRESH = 1e9;
@@ -147,6 +149,7 @@ extern "C" int qgmap_flow_to_color(const double *flow, int M, int N, double max_
         }
     }
     return QGMAP_OK;
+    });
 }
 
 // ---- PNG (imwrite replacement, gqmap_gpu_mixture.m:62): 8-bit RGB, filter 0, zlib stream of stored deflate blocks ----
@@ -176,6 +179,7 @@ static void png_chunk(std::vector<uint8_t> &out, const char *type, const std::ve
 }
 extern "C" int qgmap_write_png(const char *path, const uint8_t *rgb, int M, int N)
 {
+    return qg_guard([&]() -> int {
     if (!path || !*path || !rgb || M < 1 || N < 1) return QGMAP_ERR_ARG;
     const size_t MN = (size_t)M * N, row = 1 + 3 * (size_t)N;
     std::vector<uint8_t> raw(row * M);                                  // scanlines: filter byte 0 + interleaved RGB
@@ -209,12 +213,14 @@ extern "C" int qgmap_write_png(const char *path, const uint8_t *rgb, int M, int 
     if (!f) return QGMAP_ERR_ARG;
     const bool ok = std::fwrite(out.data(), 1, out.size(), f) == out.size();
     return (std::fclose(f) == 0 && ok) ? QGMAP_OK : QGMAP_ERR_ARG;
+    });
 }
 
 // ---- Middlebury .flo (readFlowFile.m:33-81, legacy/writeFlowFile.m): tag 202021.25 ("PIEH"), int32 width, height, then
 // row-major interleaved float32 (u,v) ----
 extern "C" int qgmap_read_flo(const char *path, int *H, int *W, double *flow)
 {
+    return qg_guard([&]() -> int {
     if (!path || !H || !W) return QGMAP_ERR_ARG;
     const size_t len = std::strlen(path);
     if (len < 4 || std::strcmp(path + len - 4, ".flo") != 0) return QGMAP_ERR_ARG;         // readFlowFile.m:44-52
@@ -228,6 +234,11 @@ extern "C" int qgmap_read_flo(const char *path, int *H, int *W, double *flow)
         *W = wh[0]; *H = wh[1];
         if (flow) {
             const size_t n = (size_t)wh[0] * wh[1];
+            // the header is untrusted: the payload it announces must really be in the file before 8n bytes are allocated for it
+            const long pos = std::ftell(f);
+            long end = -1;
+            if (pos >= 0 && std::fseek(f, 0, SEEK_END) == 0) { end = std::ftell(f); std::fseek(f, pos, SEEK_SET); }
+            if (end < 0 || (unsigned long long)(end - pos) < 8ULL * n) { std::fclose(f); return QGMAP_ERR_ARG; }
             std::vector<float> tmp(2 * n);
             ok = std::fread(tmp.data(), 4, 2 * n, f) == 2 * n;
             if (ok)
@@ -240,9 +251,11 @@ extern "C" int qgmap_read_flo(const char *path, int *H, int *W, double *flow)
     }
     std::fclose(f);
     return ok ? QGMAP_OK : QGMAP_ERR_ARG;
+    });
 }
 extern "C" int qgmap_write_flo(const char *path, const double *flow, int H, int W)
 {
+    return qg_guard([&]() -> int {
     if (!path || !flow || H < 1 || W < 1) return QGMAP_ERR_ARG;
     const size_t len = std::strlen(path);
     if (len < 4 || std::strcmp(path + len - 4, ".flo") != 0) return QGMAP_ERR_ARG;         // writeFlowFile.m:33-41
@@ -258,6 +271,7 @@ extern "C" int qgmap_write_flo(const char *path, const double *flow, int H, int 
     const int32_t wh[2] = {W, H};
     const bool ok = std::fwrite("PIEH", 1, 4, f) == 4 && std::fwrite(wh, 4, 2, f) == 2 && std::fwrite(tmp.data(), 4, 2 * n, f) == 2 * n;
     return (std::fclose(f) == 0 && ok) ? QGMAP_OK : QGMAP_ERR_ARG;
+    });
 }
 
 extern "C" const char *qgmap_status_string(int status)

@@ -23,6 +23,7 @@ struct qgmap_handle {
     long long plane = 0;
     float *I1f = nullptr;
     QgTap8 *VVf = nullptr;     // packed padded second frame (see QgIterParams::VV8)
+    QgTap16h *VVh = nullptr;   // fp16 4x4-block layout of the same frame; null unless the frame is fp16-exact (QgIterParams::VVh)
     int pitch4 = 0;
     double *I1d = nullptr, *VVd = nullptr;
     int pitchI = 0, pitchV = 0;
@@ -88,6 +89,8 @@ void qgmap_random_state(const qgmap_config &c, size_t n, int L, uint64_t seed, s
                         std::vector<double> &muv, std::vector<double> &sigu, std::vector<double> &sigv);
 struct qgmap_group;
 qgmap_handle *qgmap_group_band(qgmap_group *g, int b);           // band b's handle (monitoring kernels of qgmap_group_solve)
+
+#include "qgmap_guard.h"
 
 extern thread_local long long g_solve_launches;
 extern thread_local float g_solve_ms;

@@ -2,6 +2,7 @@
 // and the device-side getVV.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 
 // ---- layout conversion kernels (MATLAB column-major fp64 at the boundary <-> private row-major planes) ------------
 // src: column-major fp64 [rows x cols x planes]; dst: row-major T planes with pitch; copies rows [r0,r1) to local rows.
@@ -81,4 +82,32 @@ static __global__ void qgmap_pack8_kernel(const double *__restrict__ VV, int pit
     float4 *o = out + 2 * ((long long)y * pitch8 + x);
     o[0] = make_float4(g(y, x), g(y + 1, x), g(y, x + 1), g(y + 1, x + 1));
     o[1] = make_float4(g(y, x + 2), g(y + 1, x + 2), g(y, x + 3), g(y + 1, x + 3));
+}
+
+// fp16 4 x 4 block layout (QgTap16h): out[(y*pitch8+x)] word c = (VV(y,x+c), VV(y+1,x+c)), word 4+c = (VV(y+2,x+c), VV(y+3,x+c)), zero beyond
+// the padded image.  *inexact is raised if any value of the padded frame does not survive fp64 -> fp16 -> fp64 (then the layout is
+// not used: the kernels only take it when it is bit-exact).
+static __global__ void qgmap_pack16h_kernel(const double *__restrict__ VV, int pitchV, int rows_src, int width, uint4 *__restrict__ out,
+                                            int pitch8, int rows_out, int *__restrict__ inexact)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= pitch8 || y >= rows_out) return;
+    bool bad = false;
+    auto g = [&](int r, int c) -> unsigned int {
+        if (r >= rows_src || c >= width) return 0u;
+        const double v = VV[(long long)r * pitchV + c];
+        const __half hv = __double2half(v);
+        if ((double)__half2float(hv) != v) bad = true;
+        return (unsigned int)__half_as_ushort(hv);
+    };
+    unsigned int w[8];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        w[c] = g(y, x + c) | (g(y + 1, x + c) << 16);
+        w[4 + c] = g(y + 2, x + c) | (g(y + 3, x + c) << 16);
+    }
+    uint4 *o = out + 2 * ((long long)y * pitch8 + x);
+    o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    if (bad) *inexact = 1;
 }

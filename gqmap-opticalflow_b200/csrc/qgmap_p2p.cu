@@ -122,6 +122,7 @@ void qgmap_p2p_release(qgmap_handle *h)
 
 extern "C" int qgmap_band_p2p_export(qgmap_handle *h, void *blob)
 {
+    return qg_guard([&]() -> int {
     if (!h || !blob) return QGMAP_ERR_ARG;
     QGP_CUDA(h, cudaSetDevice(h->device));
     qgmap_p2p_release(h);
@@ -145,6 +146,7 @@ extern "C" int qgmap_band_p2p_export(qgmap_handle *h, void *blob)
     std::memset(blob, 0, QGMAP_P2P_BLOB_BYTES);
     std::memcpy(blob, &b, sizeof b);
     return QGMAP_OK;
+    });
 }
 
 static int map_peer(qgmap_handle *h, const QgP2PBlob &b, bool want_bufs, void **box, void **buf0, void **buf1)
@@ -175,6 +177,7 @@ static int map_peer(qgmap_handle *h, const QgP2PBlob &b, bool want_bufs, void **
 
 extern "C" int qgmap_band_p2p_connect(qgmap_handle *h, int rank, int nranks, const void *blobs)
 {
+    return qg_guard([&]() -> int {
     if (!h || !blobs || nranks < 1 || nranks > QG_RANKS_MAX || rank < 0 || rank >= nranks) return QGMAP_ERR_ARG;
     if (!h->p2p || !h->p2p->box) QGP_FAIL(h, QGMAP_ERR_STATE, "qgmap_band_p2p_connect before qgmap_band_p2p_export");
     QGP_CUDA(h, cudaSetDevice(h->device));
@@ -223,6 +226,7 @@ extern "C" int qgmap_band_p2p_connect(qgmap_handle *h, int rank, int nranks, con
     if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
     h->p2p->connected = true;
     return QGMAP_OK;
+    });
 }
 
 void qgmap_p2p_begin_step(qgmap_handle *h)

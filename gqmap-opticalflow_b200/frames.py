@@ -100,10 +100,12 @@ def _bicubic(V, yq, xq):
     return out
 
 
-def synthetic_pair(M, N, seed=1234, flow_scale=1.0):
+def synthetic_pair(M, N, seed=1234, flow_scale=1.0, grey_levels=False):
     """Synthetic frame pair of SURVEY.md section 8d: I1 = Gaussian-blurred (sigma 1.5) uniform noise scaled to [0,255];
     ground-truth flow u = 3 sin(2 pi row/M) + 1 (horizontal), v = 2 cos(2 pi col/N) (vertical); I2 = I1 warped so that
     I2(row+v, col+u) = I1(row,col) (bicubic resampling of I1 at the inverse flow, found by fixed-point iteration).
+    grey_levels=True rounds both frames to integer grey levels 0..255, which is what the reference's drivers feed the solver
+    (double(rgb2gray(imresize(imread(...)))), optical_flow.m:8-11) -- the ground truth is then exact up to that quantisation.
     Returns I1, I2 (M x N float64, 0..255), flow (M x N x 2), and (minu,maxu,minv,maxv)."""
     rng = np.random.default_rng(seed)
     a = _gauss_blur(rng.random((M, N)), 1.5)
@@ -118,5 +120,7 @@ def synthetic_pair(M, N, seed=1234, flow_scale=1.0):
     for _ in range(30):
         pr, pc = rows - fv(pr, pc), cols - fu(pr, pc)
     I2 = _bicubic(I1, pr, pc)
+    if grey_levels:
+        I1, I2 = np.clip(np.round(I1), 0.0, 255.0), np.clip(np.round(I2), 0.0, 255.0)
     flow = np.asfortranarray(np.stack([u, v], axis=2))
     return np.asfortranarray(I1), np.asfortranarray(I2), flow, (float(u.min()), float(u.max()), float(v.min()), float(v.max()))

@@ -50,13 +50,17 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
         const double *I1, *I2; int Mo, No;
         images(prhs[3], prhs[4], &I1, &I2, &Mo, &No);
         const int its = (int)qg_field(prhs[2], "its", 1, 0);
+        if (its < 1) mexErrMsgIdAndTxt("qgmap:arg", "options.its must be >= 1.");
+        if (cfg.L < 1 || cfg.L > QGMAP_LMAX) mexErrMsgIdAndTxt("qgmap:arg", "options.L must be 1..%d.", QGMAP_LMAX);
         const int M = variant ? Mo / 4 : Mo, N = variant ? No / 4 : No, L = cfg.L;
+        const size_t n3 = (size_t)M * N * L;
         const mxArray *tf = mxGetField(prhs[2], 0, "trueFlow"), *uk = mxGetField(prhs[2], 0, "unknownIdx");
         const mxArray *ini = mxGetField(prhs[2], 0, "init");
         const double *init[7]; int have_init = 0;
         if (ini && mxIsStruct(ini)) {
             have_init = 1;
-            for (int k = 0; k < 7; ++k) init[k] = qg_real_double(mxGetField(ini, 0, kState[k]), kState[k]);
+            for (int k = 0; k < 7; ++k)         /* muu,muv,sigmau,sigmav,pn: M x N x L; rou: M x N x L x 2 x 2; w: L */
+                init[k] = qg_real_double_n(mxGetField(ini, 0, kState[k]), k < 5 ? n3 : (k == 5 ? 4 * n3 : (size_t)L), kState[k]);
         }
         const mwSize d4[4] = {(mwSize)M, (mwSize)N, (mwSize)L, 2}, d3[3] = {1, 1, (mwSize)L};
         mxArray *mu = mxCreateNumericArray(4, d4, mxDOUBLE_CLASS, mxREAL), *sg = mxCreateNumericArray(4, d4, mxDOUBLE_CLASS, mxREAL);
@@ -76,8 +80,8 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
             if (ndev > QGMAP_P2P_RANKS_MAX) mexErrMsgIdAndTxt("qgmap:arg", "options.devices lists more than %d devices.", QGMAP_P2P_RANKS_MAX);
             for (int k = 0; k < ndev; ++k) devs[k] = (int)mxGetPr(dv)[k];
         }
-        const double *tfp = tf && !mxIsEmpty(tf) ? mxGetPr(tf) : NULL;
-        const uint8_t *ukp = uk && !mxIsEmpty(uk) ? (const uint8_t *)mxGetLogicals(uk) : NULL;
+        const double *tfp = tf && !mxIsEmpty(tf) ? qg_real_double_n(tf, (size_t)Mo * No * 2, "options.trueFlow") : NULL;
+        const uint8_t *ukp = qg_logical_n(uk, (size_t)Mo * No, "options.unknownIdx");
         const uint64_t seed = (uint64_t)qg_field(prhs[2], "seed", 0, 0);
         int rc;
         if (ndev > 1)
@@ -111,9 +115,13 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
         qgmap_handle *h = get_handle(prhs[1]);
         if (!mxIsStruct(prhs[2])) mexErrMsgIdAndTxt("qgmap:arg", "S must be a struct.");
         const double *f[7];
-        for (int k = 0; k < 7; ++k) f[k] = qg_real_double(mxGetField(prhs[2], 0, kState[k]), kState[k]);
+        int M, N, L;
+        qgmap_dims(h, &M, &N, &L);
+        const size_t n3 = (size_t)M * N * L;
+        for (int k = 0; k < 7; ++k)
+            f[k] = qg_real_double_n(mxGetField(prhs[2], 0, kState[k]), k < 5 ? n3 : (k == 5 ? 4 * n3 : (size_t)L), kState[k]);
         const mxArray *al = mxGetField(prhs[2], 0, "alpha");
-        qg_check(qgmap_set_state(h, f[0], f[1], f[2], f[3], f[4], f[5], f[6], al && !mxIsEmpty(al) ? mxGetPr(al) : NULL,
+        qg_check(qgmap_set_state(h, f[0], f[1], f[2], f[3], f[4], f[5], f[6], al && !mxIsEmpty(al) ? qg_real_double_n(al, (size_t)L, "alpha") : NULL,
                                  qg_field(prhs[2], "T", 0, 0.0), (int)qg_field(prhs[2], "it", 0, 1)), h);
     } else if (!strcmp(c, "init_state")) {
         qg_nargchk(nrhs, 2, 3, nlhs, 0);
@@ -144,6 +152,7 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
         qgmap_handle *h = get_handle(prhs[1]);
         const int n = (int)mxGetScalar(prhs[2]);
         const int its = nrhs > 3 ? (int)mxGetScalar(prhs[3]) : 2147483647;
+        if (n < 0 || its < 1) mexErrMsgIdAndTxt("qgmap:arg", "step: n must be >= 0 and its >= 1.");
         mxArray *E = mxCreateDoubleMatrix(n > 0 ? n : 1, 1, mxREAL), *dm = mxCreateDoubleMatrix(n > 0 ? n : 1, 1, mxREAL),
                 *ds = mxCreateDoubleMatrix(n > 0 ? n : 1, 1, mxREAL);
         int done = 0, stopped = 0;
@@ -165,14 +174,19 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[])
         qg_nargchk(nrhs, 3, 3, nlhs, 1);
         qgmap_handle *h = get_handle(prhs[1]);
         double lp = 0;
-        qg_check(qgmap_logp(h, qg_real_double(prhs[2], "map"), &lp), h);
+        int M, N, L;
+        qgmap_dims(h, &M, &N, &L);
+        qg_check(qgmap_logp(h, qg_real_double_n(prhs[2], (size_t)M * N * 2, "map"), &lp), h);
         plhs[0] = mxCreateDoubleScalar(lp);
     } else if (!strcmp(c, "aepe")) {
         qg_nargchk(nrhs, 4, 5, nlhs, 1);
         qgmap_handle *h = get_handle(prhs[1]);
         double v = 0;
-        qg_check(qgmap_aepe(h, qg_real_double(prhs[2], "map"), qg_real_double(prhs[3], "trueFlow"),
-                            nrhs > 4 && !mxIsEmpty(prhs[4]) ? (const uint8_t *)mxGetLogicals(prhs[4]) : NULL, &v), h);
+        int M, N, L, Mo, No;
+        qgmap_dims(h, &M, &N, &L);
+        qgmap_image_dims(h, &Mo, &No);
+        qg_check(qgmap_aepe(h, qg_real_double_n(prhs[2], (size_t)M * N * 2, "map"), qg_real_double_n(prhs[3], (size_t)Mo * No * 2, "trueFlow"),
+                            nrhs > 4 ? qg_logical_n(prhs[4], (size_t)Mo * No, "unknownIdx") : NULL, &v), h);
         plhs[0] = mxCreateDoubleScalar(v);
     } else {
         mexErrMsgIdAndTxt("qgmap:arg", "unknown command '%s'.", c);

@@ -15,6 +15,21 @@ static inline const double *qg_real_double(const mxArray *a, const char *what) {
     if (!a || !mxIsDouble(a) || mxIsComplex(a)) mexErrMsgIdAndTxt("qgmap:arg", "%s must be a real double array.", what);
     return mxGetPr(a);
 }
+// a real double array with exactly `n` elements (the C ABI takes plain pointers: sizes must be checked here)
+static inline const double *qg_real_double_n(const mxArray *a, size_t n, const char *what) {
+    const double *p = qg_real_double(a, what);
+    if (mxGetNumberOfElements(a) != n)
+        mexErrMsgIdAndTxt("qgmap:arg", "%s has %lu elements, %lu expected.", what, (unsigned long)mxGetNumberOfElements(a), (unsigned long)n);
+    return p;
+}
+// options.unknownIdx / the mask of 'aepe': a LOGICAL array with `n` elements, or empty / absent (NULL)
+static inline const uint8_t *qg_logical_n(const mxArray *a, size_t n, const char *what) {
+    if (!a || mxIsEmpty(a)) return NULL;
+    if (!mxIsLogical(a)) mexErrMsgIdAndTxt("qgmap:arg", "%s must be a logical array.", what);
+    if (mxGetNumberOfElements(a) != n)
+        mexErrMsgIdAndTxt("qgmap:arg", "%s has %lu elements, %lu expected.", what, (unsigned long)mxGetNumberOfElements(a), (unsigned long)n);
+    return (const uint8_t *)mxGetLogicals(a);
+}
 static inline void qg_dims3(const mxArray *a, size_t d[3]) {
     mwSize nd = mxGetNumberOfDimensions(a);
     const mwSize *dd = mxGetDimensions(a);
@@ -58,6 +73,7 @@ static inline void qg_config_from_options(const mxArray *opt, int variant, qgmap
     cfg->tor = qg_field(opt, "tor", 0, cfg->tor); cfg->sigma_step_scale = qg_field(opt, "sigma_step_scale", 0, cfg->sigma_step_scale);
     cfg->alpha_start = (int)qg_field(opt, "alpha_start", 0, cfg->alpha_start);
     cfg->anneal_every = (int)qg_field(opt, "anneal_every", 0, cfg->anneal_every);
+    cfg->strip_rows = (int)qg_field(opt, "strip_rows", 0, cfg->strip_rows);
     const mxArray *am = mxGetField(opt, 0, "alpha_mode");
     if (am && mxIsChar(am)) {
         char *sname = mxArrayToString(am);

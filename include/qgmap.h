@@ -82,8 +82,9 @@ int qgmap_config_defaults(qgmap_config *cfg, int variant);
 int qgmap_create(const qgmap_config *cfg, const double *I1, const double *I2, int Mo, int No, qgmap_handle **out);
 int qgmap_destroy(qgmap_handle *h);
 
-/* Belief-grid dimensions of a handle. */
+/* Belief-grid dimensions of a handle; size of the frames it was created with. */
 int qgmap_dims(const qgmap_handle *h, int *M, int *N, int *L);
+int qgmap_image_dims(const qgmap_handle *h, int *Mo, int *No);
 
 /* State in/out (the arrays of gqmap_gpu_mixture.m:18-24).  The reference hard-wires a random init and
  * cannot take one; these calls are what make runs reproducible and double as checkpoint/resume.

@@ -1,6 +1,6 @@
 """A/B device-time probe of the iteration kernels (development aid): ms/iteration at a converged and at the initial state,
 for kernel selections / strip heights given as env settings.  usage: ab2.py <tag> [case,case,...] [sel;sel;...]
-  case = variant:M:N:L:K:burn      sel = name=ENV1:val,ENV2:val   (library chosen by QGMAP_LIB_PATH)"""
+  case = variant:M:N:L:K:burn[:g]  (g = frames rounded to integer grey levels)     sel = name=ENV1:val,ENV2:val   (library chosen by QGMAP_LIB_PATH)"""
 import importlib, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 pkg = importlib.import_module("gqmap-opticalflow_b200")
@@ -9,11 +9,11 @@ cases = sys.argv[2] if len(sys.argv) > 2 and sys.argv[2] else "full:480:640:3:5:
 sels = sys.argv[3] if len(sys.argv) > 3 else "walk=;tile=QGMAP_ITER:tile"
 frames = {}
 for case in cases.split(","):
-    variant, M, N, L, K, burn = case.split(":")
-    M, N, L, K, burn = int(M), int(N), int(L), int(K), int(burn)
-    if (M, N) not in frames:
-        frames[(M, N)] = pkg.synthetic_pair(M, N)
-    I1, I2, flow, (minu, maxu, minv, maxv) = frames[(M, N)]
+    parts = case.split(":")
+    variant, (M, N, L, K, burn), grey = parts[0], map(int, parts[1:6]), len(parts) > 6 and parts[6] == "g"
+    if (M, N, grey) not in frames:
+        frames[(M, N, grey)] = pkg.synthetic_pair(M, N, grey_levels=grey)
+    I1, I2, flow, (minu, maxu, minv, maxv) = frames[(M, N, grey)]
     opts = dict(K=K, L=L, temperature=0.2 if variant == "super" else 0.0, drate=0.75, epsn=1e-6, lambdad=1.0,
                 lambdas=16.0 if variant == "super" else 5.0, minu=minu, maxu=maxu, minv=minv, maxv=maxv, its=10**6)
     for sel in sels.split(";"):
@@ -34,8 +34,8 @@ for case in cases.split(","):
                 for _ in range(3):
                     r = s.step(n)
                     best = min(best, r["ms"] / n)
-                print("%-8s %-10s %-5s %4dx%-4d L=%d K=%2d burn=%4d: %8.4f ms/it  %7.3f Gpx-it/s  E=%.9e" % (
-                    tag, name, variant, M, N, L, K, burn, best, M * N / best / 1e6, r["Energy"][-1]), flush=True)
+                print("%-8s %-10s %-5s %4dx%-4d L=%d K=%2d burn=%4d%s: %8.4f ms/it  %7.3f Gpx-it/s  E=%.9e" % (
+                    tag, name, variant, M, N, L, K, burn, " grey" if grey else "     ", best, M * N / best / 1e6, r["Energy"][-1]), flush=True)
         except Exception as e:
             print("%-8s %-10s %s FAILED: %s" % (tag, name, case, e), flush=True)
         for k, v in saved.items():

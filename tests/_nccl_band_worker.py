@@ -47,6 +47,25 @@ def main():
             assert np.abs(r["Energy"] / r1["Energy"] - 1).max() < 1e-12
             assert np.abs(full["alpha"] - a["alpha"]).max() < 1e-14
             print("%s bands %s world=%d: bit-identical to the single domain, %.3f ms/it" % (transport, variant, world, r["ms"] / n), flush=True)
+    # the reference-facing call, one rank per band: dist.gqmap_gpu_mixture_bands vs gqmap_gpu_mixture on rank 0 (40 iterations: the
+    # fused exchange also runs from CUDA-graph launches; monitoring shares at it = 1, 10, 20, 30, 40)
+    Mo, No = 90, 120
+    I1, I2, flow, (minu, maxu, minv, maxv) = pkg.synthetic_pair(Mo, No)
+    unk = np.zeros((Mo, No), bool)
+    unk[40:50, 10:60] = True
+    o2 = dict(K=5, L=3, its=40, temperature=0.0, drate=0.5, epsn=1e-6, lambdad=1.0, lambdas=5.0, minu=minu, maxu=maxu, minv=minv, maxv=maxv,
+              seed=5, log_every=10, trueFlow=flow, unknownIdx=unk, alpha_start=2, alpha_scale=1e-5, device=local)
+    b = pkg.dist.gqmap_gpu_mixture_bands(o2, I1, I2, dist)
+    rb, re = pkg.dist.band_rows(Mo, rank, world)
+    if rank == 0:
+        a = pkg.gqmap_gpu_mixture(o2, I1, I2)
+        assert np.array_equal(a[0][rb:re], b[0][rb:re]) and np.array_equal(a[1][rb:re], b[1][rb:re]), "own rows of mu / sigma"
+        assert np.abs(a[2] - b[2]).max() < 1e-14
+        for k in (3, 4, 5):
+            m = ~np.isnan(a[k])
+            assert np.array_equal(np.isnan(a[k]), np.isnan(b[k])) and np.abs(b[k][m] / a[k][m] - 1).max() < 1e-11, k
+        assert m.sum() == 5
+        print("gqmap_gpu_mixture_bands world=%d: bit-identical to gqmap_gpu_mixture" % world, flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

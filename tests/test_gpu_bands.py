@@ -109,3 +109,37 @@ def test_peer_memory_transport_on_one_gpu(pkg, O, monkeypatch, variant, shape, L
         assert np.array_equal(a[f], b[f]), f
     E = np.concatenate([ra["Energy"], rb["Energy"]])
     assert np.abs(E / r1["Energy"] - 1).max() < 1e-12 and np.abs(a["alpha"] - b["alpha"]).max() < 1e-14
+
+
+class _Solo:
+    """world-size-1 stand-in for torch.distributed (rendezvous is all the band solver asks of it)."""
+    @staticmethod
+    def get_rank():
+        return 0
+
+    @staticmethod
+    def get_world_size():
+        return 1
+
+
+@pytest.mark.parametrize("variant", ["full", "super"])
+def test_band_solver_equals_one_call_solver(pkg, variant):
+    """dist.gqmap_gpu_mixture_bands -- the multi-process twin of gqmap_gpu_mixture(options.devices): the reference's loop with the
+    monitoring block evaluated where the rows live (qgmap_monitor_partial) -- returns what the one-call solver returns: same
+    beliefs bit for bit, same AEPE / Energy / logP histories incl. their NaN / zero prefill (gqmap_gpu_mixture.m:16,:52-68,:183-188)."""
+    sup = variant == "super"
+    Mo, No = (96, 128) if sup else (60, 72)
+    I1, I2, flow, (minu, maxu, minv, maxv) = pkg.synthetic_pair(Mo, No)
+    unk = np.zeros((Mo, No), bool)
+    unk[5:9, 7:30] = True
+    opts = dict(K=3, L=2, its=13, temperature=0.2 if sup else 0.0, drate=0.75, epsn=1e-6, lambdad=1.0, lambdas=5.0, minu=minu, maxu=maxu,
+                minv=minv, maxv=maxv, seed=5, log_every=4, trueFlow=flow, unknownIdx=unk, alpha_start=2, alpha_scale=1e-5)
+    fn = pkg.gqmap_gpuSuper_mix_entropy if sup else pkg.gqmap_gpu_mixture
+    a = fn(opts, I1, I2)
+    b = pkg.dist.gqmap_gpu_mixture_bands(opts, I1, I2, _Solo, variant=variant)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    for k in (3, 4, 5):
+        assert a[k].shape == b[k].shape and np.array_equal(np.isnan(a[k]), np.isnan(b[k]))
+        m = ~np.isnan(a[k])
+        assert np.abs(b[k][m] - a[k][m]).max() <= 1e-11 * np.abs(a[k][m]).max(), k
+    assert (~np.isnan(a[3])).sum() == 4                        # it = 1, 4, 8, 12

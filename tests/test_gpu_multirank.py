@@ -18,7 +18,7 @@ def test_nccl_bands_two_ranks():
            "--master-port", "29621", os.path.join("tests", "_nccl_band_worker.py")]
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("bit-identical") == 4
+    assert r.stdout.count("bit-identical") == 5
 
 
 @pytest.mark.gpu

@@ -54,3 +54,37 @@ def test_walk_vs_tiled_kernel(pkg, monkeypatch):
     assert abs(ra["Energy"][0] / rb["Energy"][0] - 1) < 1e-6
     for f in ("muu", "muv", "sigmau", "sigmav"):
         assert np.abs(a[f] - b[f]).max() < 2e-4, f
+
+
+def test_sample_paths_are_bit_identical(pkg, monkeypatch):
+    """The full-resolution kernel picks a node-sample loop per warp: clamped (near the border / wide clouds that reach it),
+    inside + tap cache (fp32 entries), inside + one-sector fp16 entries (wide beliefs on grey-level frames), 5 x 5 tap window
+    (narrow beliefs).  All evaluate gqmap_gpu_mixture.m:156-179 with the same operations in the same order, so switching the
+    optional paths off must not change a single bit -- from the wide random init and from a narrow late state."""
+    Mo, No = 120, 160
+    I1, I2, flow, (minu, maxu, minv, maxv) = pkg.synthetic_pair(Mo, No, seed=9, grey_levels=True)
+    opts = dict(K=5, L=2, temperature=0.0, drate=0.5, epsn=1e-6, lambdad=1.0, lambdas=5.0, minu=minu, maxu=maxu, minv=minv, maxv=maxv,
+                alpha_start=2, alpha_scale=1e-6)
+    with pkg.Solver(opts, I1, I2) as s:
+        s.init_state(3)
+        s.step(8)
+        wide = s.get_state()
+        s.step(6000)
+        s.step(8)
+        late = s.get_state()
+    assert np.median(late["sigmau"]) < 0.15 < np.median(wide["sigmau"])      # the two regimes really are wide and narrow
+    for env in (dict(QGMAP_TAPS="f32"), dict(QGMAP_NARROW="0"), dict(QGMAP_TAPS="f32", QGMAP_NARROW="0")):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        with pkg.Solver(opts, I1, I2) as s:
+            s.init_state(3)
+            s.step(8)
+            w2 = s.get_state()
+            s.step(6000)
+            s.step(8)
+            l2 = s.get_state()
+        for k in env:
+            monkeypatch.delenv(k)
+        for f in FIELDS:
+            assert np.array_equal(wide[f], w2[f]), (env, "wide", f)
+            assert np.array_equal(late[f], l2[f]), (env, "late", f)

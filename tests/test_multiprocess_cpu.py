@@ -22,10 +22,13 @@ def test_band_protocol_world2_gloo():
 
 def test_bench_reference_arm_under_torchrun():
     """Under torchrun only rank 0 runs and prints the reference arm; the other rank exits 0 without work."""
-    r = _torchrun(["bench.py", "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--ref-pairs", "1"], 29612)
+    r = _torchrun(["bench.py", "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0", "--band-rows", "135", "--band-cols", "240"], 29612)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "pixel-iter/s" and d["value"] > 0 and d["n_gpus"] == 2
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["cpu_baseline"]["kind"] == "port"
+    sys.path.insert(0, ROOT)
+    import bench                                     # both arms must print the same config.workload (the driver compares them)
+    assert d["config"]["workload"] == bench.WORKLOAD and d["scaling"] == "strong"
