@@ -323,7 +323,7 @@ extern "C" int qgmap_create(const qgmap_config *cfg, const double *I1, const dou
     p.step0 = cfg->step0; p.step_tau = cfg->step_tau; p.alpha_scale = cfg->alpha_scale; p.drate = cfg->drate;
     p.sig_step = (float)cfg->sigma_step_scale; p.T_floor = cfg->T_floor; p.tor = cfg->tor; p.alpha_start = cfg->alpha_start; p.alpha_mode = cfg->alpha_mode;
     p.anneal_every = cfg->anneal_every;
-    { const char *nenv = getenv("QGMAP_NARROW"); p.narrow_path = !(nenv && !strcmp(nenv, "0")); }
+    { const char *wenv = getenv("QGMAP_WIDE_REACH"); p.wide_reach = wenv ? (float)atof(wenv) : 0.5f; }
     p.ctrl = h->ctrl; p.partials = h->partials; p.gpartials = h->gpartials; p.tickets = h->tickets; p.strip_rows = strip_rows;
     QG_CUDA_C(cudaStreamSynchronize(h->stream));
     if (ensure_hist(h, 1024) != QGMAP_OK) { free_handle(h); return QGMAP_ERR_CUDA; }

@@ -141,7 +141,7 @@ struct QgIterParams {
     double *gpartials;                 // row-walking kernel: [strip rows x L][QG_NRED], second reduction level
     unsigned int *tickets;             // row-walking kernel: [strip rows x L] finished-strip counters
     int strip_rows;                    // row-walking kernel: rows one warp walks
-    int narrow_path;                   // 1: warps of narrow beliefs use the 5x5 tap window (QGMAP_NARROW=0 disables: A/B, tests)
+    float wide_reach;                  // half-extent (px) of the sample cloud from which a belief counts as wide (QGMAP_WIDE_REACH)
     int pub_row[2];                    // band == 2: global row whose updated beliefs also go to the band above [0] / below [1]; -1 = none
     const struct QgPeer *peer;         // band == 2: peer-memory exchange fused into the row-walking kernel (qgmap_peer.cuh)
     double *hist_energy, *hist_dmu, *hist_dsig;   // its entries each, index it-1
@@ -681,58 +681,6 @@ __device__ __forceinline__ float qg_node_sample_inside(const QgTap8 *__restrict_
     h01 = qg_fma2(tc.v01.p[2], qg_bc(w2.x), h01);  h23 = qg_fma2(tc.v23.p[2], qg_bc(w2.x), h23);
     h01 = qg_fma2(tc.v01.p[3], qg_bc(-n3.x), h01); h23 = qg_fma2(tc.v23.p[3], qg_bc(-n3.x), h23);
     const float v = fmaf(h23.y, -n3.y, fmaf(h23.x, w2.y, fmaf(h01.y, w1.y, h01.x * -n0.y)));
-    const float d = fmaf(-0.25f, v, I1v);
-    return qg_sqrt(fmaf(d, d, epsn));
-}
-
-// ---- narrow beliefs: the whole K x K sample cloud fits into a 2 x 2 block of cells ---------------------------------------
-// Once a belief has converged (sigma ~ 0.07 px) its samples spread over a fraction of a pixel, but they still straddle a cell
-// boundary for most beliefs, so the tap cache reloads a few times per quadrature row -- each reload a dependent L1 round trip on
-// the warp's critical path (ncu: 62% of the long-scoreboard samples of the K=5 kernel sit on the first use of freshly loaded taps).
-// Here the 5 x 5 taps that cover the 2 x 2 cells are loaded ONCE per belief; a sample in the cell right of / below the window origin
-// uses the same registers with its four weights shifted by one position (a fifth weight of exactly 0 joins at the free end).
-// The products with the zero weight are exact zeros and the remaining operations are those of qg_node_sample in the same order,
-// so the value is bit-identical.  No loads, no branches, no address arithmetic inside the quadrature loop.
-struct QgWin5 {
-    float2 r01[5], r23[5];      // window rows (0,1) and (2,3), interleaved by row inside each column like QgTap8
-    float r4[5];                // window row 4
-    int kx0, ky0;               // magic-number floor bits of the window origin cell (relative to the belief's pixel)
-};
-__device__ __forceinline__ float2 qg_ld64(const void *ptr) {
-    float2 v;
-    asm("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(ptr));
-    return v;
-}
-// lo = (x,y) of the cloud's lower corner relative to the pixel; vv_mn = &VV8[m*pitchV + n]
-__device__ __forceinline__ void qg_win5_load(QgWin5 &w, const QgTap8 *__restrict__ vv_mn, int pitchV, float2 lo)
-{
-    const float2 t = qg_add2_rm(lo, qg_bc(12582912.0f));
-    w.kx0 = __float_as_int(t.x); w.ky0 = __float_as_int(t.y);
-    const QgTap8 *e = vv_mn + ((w.ky0 - 0x4B400000) * pitchV + (w.kx0 - 0x4B400000));
-    const QgTap8 a = qg_ld256(e), c = qg_ld256(e + 2 * pitchV), g = qg_ld256(e + 4 * pitchV);
-    const float2 b = qg_ld64(e + 4), d = qg_ld64(e + 2 * pitchV + 4), h = qg_ld64(e + 4 * pitchV + 4);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { w.r01[k] = a.p[k]; w.r23[k] = c.p[k]; w.r4[k] = g.p[k].x; }
-    w.r01[4] = b; w.r23[4] = d; w.r4[4] = h.x;
-}
-__device__ __forceinline__ float qg_node_sample_win5(const QgWin5 &w, float2 x, float I1v, float epsn)
-{
-    const float2 magic = qg_bc(12582912.0f);
-    const float2 t = qg_add2_rm(x, magic);
-    const float2 fr = qg_sub2(x, qg_sub2(t, magic));
-    const bool dx = __float_as_int(t.x) != w.kx0, dy = __float_as_int(t.y) != w.ky0;     // sample in the second cell of the axis
-    float2 n0, w1, w2, n3;
-    qg_cubic_w2(fr, n0, w1, w2, n3);
-    const float a0 = -n0.x, a1 = w1.x, a2 = w2.x, a3 = -n3.x, b0 = -n0.y, b1 = w1.y, b2 = w2.y, b3 = -n3.y;
-    const float wx0 = dx ? 0.0f : a0, wx1 = dx ? a0 : a1, wx2 = dx ? a1 : a2, wx3 = dx ? a2 : a3, wx4 = dx ? a3 : 0.0f;
-    const float wy0 = dy ? 0.0f : b0, wy1 = dy ? b0 : b1, wy2 = dy ? b1 : b2, wy3 = dy ? b2 : b3, wy4 = dy ? b3 : 0.0f;
-    float2 h01 = qg_mul2(w.r01[0], qg_bc(wx0)), h23 = qg_mul2(w.r23[0], qg_bc(wx0));
-    float h4 = w.r4[0] * wx0;
-    h01 = qg_fma2(w.r01[1], qg_bc(wx1), h01); h23 = qg_fma2(w.r23[1], qg_bc(wx1), h23); h4 = fmaf(w.r4[1], wx1, h4);
-    h01 = qg_fma2(w.r01[2], qg_bc(wx2), h01); h23 = qg_fma2(w.r23[2], qg_bc(wx2), h23); h4 = fmaf(w.r4[2], wx2, h4);
-    h01 = qg_fma2(w.r01[3], qg_bc(wx3), h01); h23 = qg_fma2(w.r23[3], qg_bc(wx3), h23); h4 = fmaf(w.r4[3], wx3, h4);
-    h01 = qg_fma2(w.r01[4], qg_bc(wx4), h01); h23 = qg_fma2(w.r23[4], qg_bc(wx4), h23); h4 = fmaf(w.r4[4], wx4, h4);
-    const float v = fmaf(h4, wy4, fmaf(h23.y, wy3, fmaf(h23.x, wy2, fmaf(h01.y, wy1, h01.x * wy0))));
     const float d = fmaf(-0.25f, v, I1v);
     return qg_sqrt(fmaf(d, d, epsn));
 }

@@ -193,24 +193,22 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
     const float pn = is_out ? qg_lds(base + F_PN * fstr + idx) : 0.f;
     QgSpectral sp;
     sp.set(pn);
-    //      Narrow as well -- the cloud spans at most two cells per axis, eight pixels away from the far borders -- for every belief
-    //      of the warp -> the 5 x 5 tap window is loaded once and the sample loop has no loads at all (qg_node_sample_win5).
-    bool all_inside = false, all_narrow = false;
-    float2 cloud_lo = make_float2(0.f, 0.f);
+    //      Wide -- the cloud reaches more than a pixel to either side, so nearly every sample lands in a new cell -- for at least half
+    //      of the warp's beliefs, on a frame that has the fp16 4 x 4-block layout -> one-sector gather without a tap cache
+    //      (qg_node_sample_wide); narrower warps re-use taps often enough for the cache to win (profiles/r02_paths_ab.txt).
+    bool all_inside = false, go_wide = false;
     if (!SUPER) {
-        bool inside = true, narrow = true;
+        bool inside = true, wide = false;
         if (is_out) {
             const int Kq = KT > 0 ? KT : p.K;
             const float reach = 1.4142135623730951f * p.tab.X[Kq - 1] * (fabsf(sp.s) + fabsf(sp.t)) * 1.0001f;
             const float ex = fmaf(reach, sigu, 0.01f), ey = fmaf(reach, sigv, 0.01f);
             inside = (muu - ex >= (float)(-n)) && (muu + ex <= (float)(p.No - 2 - n)) &&
                      (muv - ey >= (float)(-m)) && (muv + ey <= (float)(p.Mo - 2 - m));
-            cloud_lo = make_float2(muu - ex, muv - ey);
-            narrow = inside && (floorf(muu + ex) - floorf(cloud_lo.x) <= 1.0f) && (floorf(muv + ey) - floorf(cloud_lo.y) <= 1.0f) &&
-                     (muu + ex <= (float)(p.No - 8 - n)) && (muv + ey <= (float)(p.Mo - 8 - m));
+            wide = fmaxf(ex, ey) >= p.wide_reach;
         }
         all_inside = __all_sync(0xffffffffu, inside);
-        all_narrow = __all_sync(0xffffffffu, narrow) && p.narrow_path;
+        go_wide = all_inside && p.VVh && __popc(__ballot_sync(0xffffffffu, wide)) >= 16;
     }
 
     float red[QG_NRED] = {0.f, 0.f, 0.f, 0.f};
@@ -252,13 +250,7 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
             });
         } else {
             const float I1v = __ldg(p.I1 + (long long)m * p.pitchI + n);
-            if (all_narrow) {
-                QgWin5 win;
-                qg_win5_load(win, p.VV8 + (long long)m * p.pitchV + n, p.pitchV, cloud_lo);
-                mo = qg_quadrature<KT>(p.tab, p.K, muu, muv, sigu, sigv, sp, -p.lambdad, [&](float2 x) {
-                    return qg_node_sample_win5(win, x, I1v, p.epsn);
-                });
-            } else if (all_inside && p.VVh) {          // wide beliefs on an fp16-exact frame: one sector per sample, no tap cache
+            if (go_wide) {                             // wide beliefs on an fp16-exact frame: one sector per sample, no tap cache
                 const QgTap16h *vh_mn = p.VVh + (long long)m * p.pitchV + n;
                 const int koff = -0x4B400000 * (p.pitchV + 1);
                 mo = qg_quadrature<KT>(p.tab, p.K, muu, muv, sigu, sigv, sp, -p.lambdad, [&](float2 x) {

@@ -205,6 +205,29 @@ def run(cfg, I1, VV, state, it, its, nsteps):
     return n, itc.value, bool(stopped.value), E[:n], dm[:n], ds[:n]
 
 
+def interp2_cubic_refine(V, k):
+    """interp2(V,k,'cubic') restated (see qo_interp2_cubic_refine)."""
+    V = _f64(V)
+    M, N = V.shape
+    out = np.zeros(((M - 1) * 2 ** k + 1, (N - 1) * 2 ** k + 1), order="F")
+    lib().qo_interp2_cubic_refine(_p(V), C.c_int(M), C.c_int(N), C.c_int(k), _p(out))
+    return out
+
+
+_cont_keep = None
+
+
+def set_nearest_lookup(I2_cont=None, rfc=6):
+    """legacy/gqmap_ctf.m:96: data term = nearest lookup into I2_cont (None switches back to the exact bicubic sample)."""
+    global _cont_keep
+    if I2_cont is None:
+        lib().qo_set_nearest_lookup(None, 0, 0, 0)
+        _cont_keep = None
+        return
+    _cont_keep = _f64(I2_cont)
+    lib().qo_set_nearest_lookup(_p(_cont_keep), C.c_int(_cont_keep.shape[0]), C.c_int(_cont_keep.shape[1]), C.c_int(2 ** rfc))
+
+
 def update_alpha(cfg, state, dalpha, step):
     st = state.c_struct()
     dalpha = np.ascontiguousarray(dalpha, dtype=np.float64)

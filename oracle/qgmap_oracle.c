@@ -106,12 +106,20 @@ void qo_get_vv(const double *V, int M, int N, double *VV)
  * node_pot  gqmap_gpu_mixture.m:156-179 (super :171-194 uses Mo,No -- here c->Mo,c->No always are the
  * image dims).  x1 = horizontal (column) displacement, x2 = vertical (row) displacement.
  * ---------------------------------------------------------------------------------------------- */
-double qo_node_pot(const qo_config *c, const double *I1, const double *VV, double x1, double x2, int i, int j)
+/* legacy/gqmap_ctf.m:10,66,96 -- the coarse-to-fine solver's data term: a NEAREST lookup into the second frame upsampled 2^rfc
+ * times per axis by interp2(I2,rfc,'cubic') ("I2_cont"), instead of an exact bicubic sample.  Optional (off unless set): */
+static const double *g_cont = 0;
+static int g_cont_MM = 0, g_cont_NN = 0, g_cont_rfc2 = 0;
+void qo_set_nearest_lookup(const double *I2_cont, int MM, int NN, int rfc2)
 {
-    const int M = c->Mo, N = c->No;
+    g_cont = I2_cont; g_cont_MM = MM; g_cont_NN = NN; g_cont_rfc2 = rfc2;
+}
+static double matlab_round(double x) { return x < 0.0 ? -floor(-x + 0.5) : floor(x + 0.5); }
+
+/* The bicubic sample of :156-176 at (row Yq, column Xq), 1-based, already clamped to the image. */
+static double bicubic_vv(const double *VV, int M, int N, double Xq, double Yq)
+{
     const long M2 = M + 2;
-    double Xq = fmin(fmax((double)j + x1, 1.0), (double)N);                 /* :157 */
-    double Yq = fmin(fmax((double)i + x2, 1.0), (double)M);                 /* :158 */
     double ix, iy;
     if (Xq <= 1.0) ix = 1.0; else if (Xq <= (double)(N - 1)) ix = floor(Xq); else ix = (double)(N - 1);  /* :160 */
     if (Yq <= 1.0) iy = 1.0; else if (Yq <= (double)(M - 1)) iy = floor(Yq); else iy = (double)(M - 1);  /* :161 */
@@ -131,7 +139,38 @@ double qo_node_pot(const qo_config *c, const double *I1, const double *VV, doubl
     Vq = Vq + P[iy3] * ss * t0 + P[iy3 + 1] * ss * t1 + P[iy3 + 2] * ss * t2 + P[iy3 + 3] * ss * t3;
     ss = (so - 1.0) * so * so;                                                                   /* :174 */
     Vq = Vq + P[iy4] * ss * t0 + P[iy4 + 1] * ss * t1 + P[iy4 + 2] * ss * t2 + P[iy4 + 3] * ss * t3;
-    Vq = Vq / 4.0;                                                                               /* :176 */
+    return Vq / 4.0;                                                                             /* :176 */
+}
+
+/* interp2(V,k,'cubic') restated: MATLAB's classic cubic-convolution interp2 (toolbox/matlab/polyfun/interp2.m, subfunction `cubic`;
+ * third party, not shipped with the reference) pads V by one quadratically extrapolated ring (3a-3b+c) and applies the Keys
+ * a=-0.5 weights -- which is exactly what the reference's own getVV (:191-208) and node_pot (:160-176) hand-copy.  So the refined
+ * grid is evaluated with those two restated functions; out is ((M-1)*2^k+1) x ((N-1)*2^k+1), column-major. */
+void qo_interp2_cubic_refine(const double *V, int M, int N, int k, double *out)
+{
+    const int r = 1 << k, MM = (M - 1) * r + 1, NN = (N - 1) * r + 1;
+    double *VV = (double *)malloc(sizeof(double) * (size_t)(M + 2) * (N + 2));
+    qo_get_vv(V, M, N, VV);
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < NN; ++b)
+        for (int a = 0; a < MM; ++a)
+            out[a + (size_t)MM * b] = bicubic_vv(VV, M, N, 1.0 + (double)b / r, 1.0 + (double)a / r);
+    free(VV);
+}
+
+double qo_node_pot(const qo_config *c, const double *I1, const double *VV, double x1, double x2, int i, int j)
+{
+    const int M = c->Mo, N = c->No;
+    double Vq;
+    if (g_cont) {                                                                                /* legacy/gqmap_ctf.m:96 */
+        long a = (long)fmin(fmax(matlab_round(((double)i + x2 - 1.0) * g_cont_rfc2 + 1.0), 1.0), (double)g_cont_MM);
+        long b = (long)fmin(fmax(matlab_round(((double)j + x1 - 1.0) * g_cont_rfc2 + 1.0), 1.0), (double)g_cont_NN);
+        Vq = g_cont[(a - 1) + (size_t)g_cont_MM * (b - 1)];
+    } else {
+        double Xq = fmin(fmax((double)j + x1, 1.0), (double)N);                 /* :157 */
+        double Yq = fmin(fmax((double)i + x2, 1.0), (double)M);                 /* :158 */
+        Vq = bicubic_vv(VV, M, N, Xq, Yq);
+    }
     double d = I1[(i - 1) + (long)M * (j - 1)] - Vq;
     return -c->lambdad * sqrt(c->epsn + d * d);                                                  /* :178 */
 }

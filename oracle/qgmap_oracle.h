@@ -64,6 +64,10 @@ int  qo_gauss_hermite(int n, double *x, double *w);
 void qo_get_vv(const double *V, int M, int N, double *VV);
 /* gqmap_gpu_mixture.m:156-179 ; i,j 1-based image row/col */
 double qo_node_pot(const qo_config *c, const double *I1, const double *VV, double x1, double x2, int i, int j);
+/* legacy/gqmap_ctf.m:10,96: optional nearest lookup into I2_cont = interp2(I2,rfc,'cubic') as the data term (NULL switches it off);
+ * interp2(V,k,'cubic') restated through getVV + the weights of node_pot (what the reference hand-copies from interp2.m) */
+void qo_set_nearest_lookup(const double *I2_cont, int MM, int NN, int rfc2);
+void qo_interp2_cubic_refine(const double *V, int M, int N, int k, double *out);
 /* gqmap_gpu_mixture.m:180-182 */
 double qo_edge_pot(const qo_config *c, double x1, double x2);
 
