@@ -61,7 +61,11 @@ typedef struct {
     double alpha_scale;             /* 1e-7 (:83)                                                          */
     double T_floor;                 /* 0.001 (S:72)                                                        */
     double tor;                     /* 1e-4 (:25) stop when mean|dmu_u| < tor                              */
-    double sigma_step_scale;        /* 1 (:43-44); legacy/gqmap_ctf.m:48-49 steps sigma with step*0.3      */
+    double sigma_step_scale;        /* 1 (:43-44); legacy/gqmap_ctf.m:34-35 steps sigma with step*0.3.  NOTE: run with
+                                       gqmap_ctf's constants the library still samples the second frame with the exact
+                                       bicubic of :156-179, NOT gqmap_ctf's nearest lookup into a 64x upsampled frame
+                                       (legacy/gqmap_ctf.m:10,96) -- a deliberate difference, measured in
+                                       tests/test_refsrc_ctf.py                                            */
     int32_t alpha_start;            /* alpha updates when it > 500 (:50)                                   */
     int32_t alpha_mode;             /* QGMAP_ALPHA_*                                                       */
     int32_t anneal_every;           /* 0 = never (full-res, :73 commented) ; 500 (S:72)                    */
