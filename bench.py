@@ -293,6 +293,13 @@ def run_ours(args):
         prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
         pass
+    if world > 1 and prof:                                             # a band: the one-of-eight capture at N=8, else the whole-frame capture scaled
+        band = prof.get("band_of_8", {})
+        if world == 8 and band:
+            prof = dict(prof, **band)
+        else:
+            prof = dict(prof, dram_bytes_per_launch=prof.get("dram_bytes_per_launch", 0) / world,
+                        source=prof.get("source", "") + " / %d (whole-frame capture scaled to one band)" % world)
     out_line = {
         "metric": "QGMAP pixel-iterations/s", "value": value, "unit": "pixel-iter/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
@@ -325,6 +332,7 @@ def run_ours(args):
                      "init_phase": {"ms_per_launch": init_ms, "frac": px_launch * F / (init_ms * 1e-3) / 1e12 / fp32_meas,
                                     "iterations": "1..%d" % args.init_iters},
                      "fma_pipe_active": prof.get("fma_pipe_active_pct"), "issue_active": prof.get("issue_active_pct"),
+                     "l1_data_stage_active": prof.get("l1_data_stage_active_pct"),
                      "traffic": prof.get("dram_bytes_per_launch"), "traffic_source": prof.get("source"),
                      "hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"}},

@@ -72,6 +72,17 @@ template <int KT, bool SUPER, bool DUMP>
 static void launch_inst(const qgmap_handle *h) {
     if (!SUPER && h->walk) { qgmap_walk_kernel<KT, DUMP><<<h->grid, 32, 0, h->stream>>>(h->params); return; }
     const dim3 block(QG_TW, QgTile<KT, SUPER>::TH + 1);
+    if (h->pdl && !DUMP && h->nranks <= 1) {             // programmatic dependent launch: the next iteration's launch overlaps this one's tail (qg_pdl_enter)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = h->grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (h->lanes_per_belief == 4) cudaLaunchKernelEx(&cfg, qgmap_iter_kernel_g4<KT, SUPER, DUMP>, h->params);
+        else cudaLaunchKernelEx(&cfg, qgmap_iter_kernel<KT, SUPER, DUMP>, h->params);
+        return;
+    }
     if (h->lanes_per_belief == 4) qgmap_iter_kernel_g4<KT, SUPER, DUMP><<<h->grid, block, 0, h->stream>>>(h->params);
     else qgmap_iter_kernel<KT, SUPER, DUMP><<<h->grid, block, 0, h->stream>>>(h->params);
 }
@@ -238,7 +249,8 @@ extern "C" int qgmap_create(const qgmap_config *cfg, const double *I1, const dou
         qgmap_import_kernel<double><<<tg, tb, 0, h->stream>>>(h->stage, Mo, No, 1, h->I1d, h->pitchI, 0, 0, Mo, 0);
         QG_CUDA_C(cudaStreamSynchronize(h->stream));            // stage is reused for I2
         QG_CUDA_C(cudaMemcpyAsync(h->stage, I2, MoNo * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        qgmap_vv_rows_kernel<<<(No + 2 + 127) / 128, 128, 0, h->stream>>>(h->stage, Mo, No, h->VVd, h->pitchV);
+        qgmap_import_kernel<double><<<tg, tb, 0, h->stream>>>(h->stage, Mo, No, 1, h->VVd + h->pitchV + 1, h->pitchV, 0, 0, Mo, 0);
+        qgmap_vv_rows_kernel<<<(No + 2 + 127) / 128, 128, 0, h->stream>>>(Mo, No, h->VVd, h->pitchV);
         qgmap_vv_cols_kernel<<<(Mo + 2 + 127) / 128, 128, 0, h->stream>>>(Mo, No, h->VVd, h->pitchV);
         qgmap_cast_kernel<float><<<256, 256, 0, h->stream>>>(h->I1d, h->I1f, (long long)nI);
         qgmap_pack8_kernel<<<dim3((h->pitch4 + 127) / 128, Mo + 2), 128, 0, h->stream>>>(h->VVd, h->pitchV, Mo + 2, No + 2,
@@ -284,6 +296,8 @@ extern "C" int qgmap_create(const qgmap_config *cfg, const double *I1, const dou
     {
         const char *env = getenv("QGMAP_ITER");
         h->walk = !sup && h->lanes_per_belief == 1 && env && !strcmp(env, "walk");
+        const char *penv = getenv("QGMAP_PDL");
+        h->pdl = penv && atoi(penv) != 0;
         if (h->walk) {
             int ndev_sm = 148;
             cudaDeviceGetAttribute(&ndev_sm, cudaDevAttrMultiProcessorCount, h->device);

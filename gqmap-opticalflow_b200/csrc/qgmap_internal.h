@@ -32,6 +32,7 @@ struct qgmap_handle {
     QgCtrl *ctrl = nullptr, *ctrl_host = nullptr;
     double *partials = nullptr, *gpartials = nullptr;
     unsigned int *tickets = nullptr;
+    bool pdl = false;             // iteration launches carry the programmatic-serialization attribute (QGMAP_PDL; qg_pdl_enter)
     bool walk = false;            // full-resolution variant: row-walking kernel (qgmap_walk.cuh) instead of the tiled one
     double *hist[3] = {nullptr, nullptr, nullptr};
     int hist_cap = 0;

@@ -17,6 +17,14 @@
 
 __device__ __forceinline__ float qg_clamp(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 
+// Programmatic dependent launch (qgmap_handle::pdl): iteration t+1 is launched while iteration t still runs and waits HERE, before it
+// reads anything iteration t writes (control block, beliefs), until that grid has completed and flushed; it then lets iteration t+2
+// be launched.  Both instructions are no-ops in a launch without the programmatic-serialization attribute.
+__device__ __forceinline__ void qg_pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // Tile rows are issued in the order 0, last, 1, 2, ...: tiles touching the top/bottom image border hold the samples that get
 // clamped to the image (the slow path of the super-pixel variant); starting them first keeps them out of the launch's tail.
 __device__ __forceinline__ int qg_tile_row() {
@@ -121,6 +129,7 @@ __global__ void __launch_bounds__(QG_TW *(QgTile<KT, SUPER>::TH + 1), QgTile<KT,
 qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
 {
     QgCtrl *ctrl = p.ctrl;
+    qg_pdl_enter();
     if (!DUMP && ctrl->stop) return;
     const int it = ctrl->it;
     const float *__restrict__ in = p.buf[(it - 1) & 1];
@@ -313,6 +322,7 @@ __global__ void __launch_bounds__(QG_TW *(QgTile<KT, SUPER>::TH + 1), QgTile<KT,
 qgmap_iter_kernel_g4(const __grid_constant__ QgIterParams p)
 {
     QgCtrl *ctrl = p.ctrl;
+    qg_pdl_enter();
     if (!DUMP && ctrl->stop) return;
     const int it = ctrl->it;
     const float *__restrict__ in = p.buf[(it - 1) & 1];

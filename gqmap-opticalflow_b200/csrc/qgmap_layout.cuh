@@ -42,17 +42,14 @@ __global__ void qgmap_export_kernel(const T *__restrict__ src, int pitch, long l
     }
 }
 
-// getVV (gqmap_gpu_mixture.m:191-208) on the device, fp64 row-major: first pass copies the interior and extrapolates
-// the top/bottom rows of every column (corners still zero), second pass the left/right columns of every row.
-static __global__ void qgmap_vv_rows_kernel(const double *__restrict__ I2 /* col-major Mo x No */, int Mo, int No,
-                                     double *__restrict__ VV, int pitchV)
+// getVV (gqmap_gpu_mixture.m:191-208) on the device, fp64 row-major.  The interior is the frame itself (qgmap_import_kernel into
+// VV + pitchV + 1, a coalesced transpose); this pass extrapolates the top/bottom rows of every padded column (the corner inputs are
+// still zero, as in the reference: VV is zero-filled before), the next one the left/right columns of every row.
+static __global__ void qgmap_vv_rows_kernel(int Mo, int No, double *__restrict__ VV, int pitchV)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;            // padded column 0..No+1
     if (c > No + 1) return;
-    auto in = [&](int r) -> double {                                // padded row r in 1..Mo, padded col c
-        return (c >= 1 && c <= No) ? I2[(r - 1) + (long long)Mo * (c - 1)] : 0.0;
-    };
-    for (int r = 1; r <= Mo; ++r) VV[(long long)r * pitchV + c] = in(r);
+    auto in = [&](int r) -> double { return VV[(long long)r * pitchV + c]; };             // padded row r in 1..Mo
     VV[c] = (3.0 * in(1) - 3.0 * in(2)) + in(3);                                          // :201
     VV[(long long)(Mo + 1) * pitchV + c] = (3.0 * in(Mo) - 3.0 * in(Mo - 1)) + in(Mo - 2); // :202
 }
