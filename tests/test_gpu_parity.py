@@ -20,7 +20,7 @@ def lanes_per_belief(request, monkeypatch):
 
 GRAD_RTOL = 3e-4        # of max|array| (fp32 vs fp64, cancellation in the score-function sums)
 GRAD_ETOL = 1e-3        # per element: relative to the gradient's own magnitude ...
-GRAD_EFLOOR = 3e-4      # ... plus this times the 1/(o*pr) amplification (the same form as _assert_state_close's step bound)
+GRAD_EFLOOR = 2e-4      # ... plus this times the 1/(o*pr) amplification (the same form as _assert_state_close's step bound)
 
 
 def _rel(a, b):
