@@ -59,18 +59,23 @@ __device__ __forceinline__ void qg_block_finish(const QgIterParams &p, QgCtrl *c
 #pragma unroll
         for (int w = 1; w <= TH; ++w) s += sh_red[w][tid];
         p.partials[(size_t)blk * QG_NRED + tid] = s;
-        if (!DUMP) __threadfence();          // only the four writers fence (a MEMBAR.SC per thread of the CTA cost ~4% of the stall samples)
     }
     if (DUMP) return;
 
-    __syncthreads();
-    if (tid == 0) {
-        unsigned int t = atomicAdd(&ctrl->ticket, 1u);
-        sh_last = (t == nblk_l * gridDim.z - 1);
+    // Ticket: the four writers and the ticket thread sit in warp 0, so a warp barrier orders their stores before lane 0's RELEASE
+    // increment (cumulative over the barrier) -- no CTA-wide barrier between the stores and the ticket, and no sequentially-consistent
+    // fence (the MEMBAR.SC + the extra barrier were 4-7% of the warp samples, profiles/r02_iter_full_L3K5_*_v12_*).
+    if (tid < 32) {
+        __syncwarp();
+        if (tid == 0) {
+            unsigned int t;
+            asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(&ctrl->ticket) : "memory");
+            sh_last = (t == nblk_l * gridDim.z - 1);
+        }
     }
     __syncthreads();
     if (!sh_last) return;
-    __threadfence();
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");       // acquire side: every block's partials are visible after its ticket
     __shared__ double sh_sum[QG_LMAX * QG_NRED];
     const int nthr = QG_TW * (TH + 1), warp = tid >> 5, lane = tid & 31, nwarp = nthr / 32;
     for (int ll = 0; ll < p.L; ++ll) {
