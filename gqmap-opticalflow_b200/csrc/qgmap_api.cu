@@ -71,7 +71,7 @@ extern "C" int qgmap_config_defaults(qgmap_config *c, int variant)
 template <int KT, bool SUPER, bool DUMP>
 static void launch_inst(const qgmap_handle *h) {
     if (!SUPER && h->walk) { qgmap_walk_kernel<KT, DUMP><<<h->grid, 32, 0, h->stream>>>(h->params); return; }
-    const dim3 block(QG_TW, QgTile<KT, SUPER>::TH + 1);
+    const dim3 block(QG_TW, h->lanes_per_belief == 4 ? QgTileG4<KT, SUPER>::NW : QgTile<KT, SUPER>::TH + QgTile<KT, SUPER>::W0);
     if (h->pdl && !DUMP && h->nranks <= 1) {             // programmatic dependent launch: the next iteration's launch overlaps this one's tail (qg_pdl_enter)
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = h->grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
@@ -287,7 +287,7 @@ extern "C" int qgmap_create(const qgmap_config *cfg, const double *I1, const dou
         if (h->lanes_per_belief != 4) h->lanes_per_belief = 1;
     }
     const int tw = h->lanes_per_belief == 4 ? QG_CW - 1 : QG_TW - 1;
-    const int th = qg_tile_rows(h->K, sup);
+    const int th = qg_tile_rows(qg_template_k(h->K), sup);
     h->grid = dim3((N - 2 + tw - 1) / tw, std::max((out_rows + th - 1) / th, 1), h->L);
     // QGMAP_ITER=walk selects the row-walking form of the full-resolution kernel (qgmap_walk.cuh: one warp per strip of 31 columns
     // x strip_rows rows, no CTA barrier; ~15% fewer instructions but it needs 96+ registers, measured 3-7% behind the tiled kernel

@@ -16,26 +16,38 @@
 #define QG_LMAX 10
 #define QG_KMAX 32
 #define QG_TW 32            // lanes per tile row (lane 0 = halo column)
-// Tile shape per kernel instantiation: a CTA is QG_TW lanes x (TH+1) warps (warp 0 = halo row), compiled for MINB resident CTAs
-// per SM.  Measured on B200 (profiles/r01_tile_ab.txt): small quadrature orders (K <= 5) are latency-bound and gain from 4 CTAs
-// of 8 warps at 64 registers (+4% K=5, +12% K=3); K >= 7 is FMA-pipe/issue-bound and keeps 3 CTAs of 9 warps at 72 registers.
-// The super-pixel variant has few, heavy beliefs: smaller CTAs, so a straggler warp (border blocks take a slower clamped path)
-// holds back fewer warps at the block reduction.
-#ifndef QG_SMALLK_TH
-#define QG_SMALLK_TH 7
+// Tile shape per kernel instantiation: a CTA is QG_TW lanes x (TH + W0) warps, compiled for MINB resident CTAs per SM.  W0 = 1: warp 0
+// is a halo warp (the row above the tile; it evaluates only the down edge whose endpoint-2 gradient the first output row needs and
+// then idles at the block reduction).  W0 = 0: no halo warp -- the first output row evaluates that edge itself, after the exchange
+// barrier, through the same call site as its own down edge (qgmap_iter.cuh).  Measured on B200 (profiles/r01_tile_ab.txt,
+// profiles/r02_paths_ab.txt): K <= 5 is latency-bound and gains from 4 CTAs of 8 warps at 64 registers; without the halo warp all eight
+// own rows (K=5: +5.9% at 4K, +3.4% converged); K=3 keeps the halo warp (-2.5% without: its edges are half of a thread's work);
+// K >= 7: 3 CTAs of 8 warps (+1.5%); run-time K keeps 3 CTAs of 9 warps.  The super-pixel variant has few, heavy beliefs: smaller CTAs, so a straggler warp (border blocks
+// take a slower clamped path) holds back fewer warps at the block reduction.
+#ifndef QG_HALO_WARP
+#define QG_HALO_WARP 0      // 1: halo warp in every instantiation (A/B builds)
+#endif
+#ifndef QG_SMALLK_MINB
 #define QG_SMALLK_MINB 4
 #endif
 #ifndef QG_SUPER_TH
 #define QG_SUPER_TH 4
 #define QG_SUPER_MINB 4
 #endif
+#ifndef QG_SUPER_MINB_NOHALO
+#define QG_SUPER_MINB_NOHALO 5      // four-lane kernel without a halo warp: 5 CTAs x 4 warps at 96 registers
+#endif
+__host__ __device__ constexpr int qg_template_k(int K) { return (K == 3 || K == 5 || K == 7 || K == 9 || K == 11) ? K : 0; }   // 0: run-time K
+// K below: the template K (qg_template_k).  Halo warp kept for K = 3 (-2.5% without), run-time K (-4.7%) and the one-lane super-pixel form.
+__host__ __device__ constexpr int qg_tile_halo(int K, bool super) { return (QG_HALO_WARP || super || K == 3 || K == 0) ? 1 : 0; }
+__host__ __device__ constexpr int qg_tile_rows(int K, bool super) {      // rows per tile
+    return super ? QG_SUPER_TH : 8 - ((K == 3 || K == 5) ? qg_tile_halo(K, super) : 0);
+}
 template <int KT, bool SUPER> struct QgTile {
-    static constexpr int TH = SUPER ? QG_SUPER_TH : ((KT > 0 && KT <= 5) ? QG_SMALLK_TH : 8);
+    static constexpr int W0 = qg_tile_halo(KT, SUPER);
+    static constexpr int TH = qg_tile_rows(KT, SUPER);
     static constexpr int MINB = SUPER ? QG_SUPER_MINB : ((KT > 0 && KT <= 5) ? QG_SMALLK_MINB : 3);
 };
-__host__ __device__ constexpr int qg_tile_rows(int K, bool super) {      // host mirror of QgTile<K,SUPER>::TH (template K set)
-    return super ? QG_SUPER_TH : ((K == 3 || K == 5) ? QG_SMALLK_TH : 8);
-}
 #define QG_TH_MAX 8
 #define QG_NRED 4           // block-reduced scalars: energy, dalpha, sum|G_muu|, sum|G_sigu|
 
@@ -559,19 +571,25 @@ struct QgSpectral2 {
 
 struct QgGrad2 { float2 da, du1, du2, do1, do2, dp, Ei; };
 
-// m*: moments of the POTENTIAL already scaled by -lambda/pi.  kT = +T for edges.
-__device__ __forceinline__ QgGrad2 qg_epilogue2(float2 E, float2 MI, float2 MJ, float2 MII, float2 MJJ, float2 MB, const QgSpectral2 &sp,
-                                                float a, float2 o1, float2 o2, float2 p, float kT)
+// Raw moments of the potential and their common scale sc = -lambda/pi.  kT = +T for edges.
+// ptxas contracts a packed mul.rn.f32x2 that feeds an add/sub.rn.f32x2 into FFMA2 (also under -fmad=false), and may do so differently in
+// two inlined copies of this function; the iteration kernel evaluates down edges at two call sites whose results must agree bit for bit
+// (qgmap_iter.cuh), so no packed product feeds a packed sum here: sums are formed before the scaling and every multiply-add is written
+// as the FMA it is meant to be.
+__device__ __forceinline__ QgGrad2 qg_epilogue2(float2 Er, float2 MIr, float2 MJr, float2 MIIr, float2 MJJr, float2 MBr, float2 sc,
+                                                const QgSpectral2 &sp, float a, float2 o1, float2 o2, float2 p, float kT)
 {
     const float sqrt2 = 1.4142135623730951f, const1 = 2.8378770664093453f;   // 1+log(2pi)
     QgGrad2 g;
-    const float2 A = qg_add2(MII, MJJ), D = qg_sub2(MII, MJJ);
+    const float2 Ar = qg_add2(MIIr, MJJr);
+    const float2 E = qg_mul2(Er, sc), MI = qg_mul2(MIr, sc), MJ = qg_mul2(MJr, sc);
+    const float2 D = qg_mul2(qg_sub2(MIIr, MJJr), sc);
     const float2 S1 = qg_fma2(sp.c1, MI, qg_mul2(sp.c2, MJ));
     const float2 S2 = qg_fma2(sp.c2, MI, qg_mul2(sp.c1, MJ));
-    const float2 EmA = qg_sub2(E, A);
-    const float2 Sp = qg_fma2(p, EmA, qg_add2(MB, MB));
-    const float2 Dq = qg_mul2(D, make_float2(qg_rcp(sp.q.x), qg_rcp(sp.q.y)));
-    const float2 T1 = qg_sub2(Dq, EmA), T2 = qg_neg2(qg_add2(Dq, EmA));
+    const float2 EmA = qg_mul2(qg_sub2(Er, Ar), sc);
+    const float2 Sp = qg_fma2(p, EmA, qg_mul2(qg_mul2(MBr, sc), qg_bc(2.0f)));
+    const float2 rq = make_float2(qg_rcp(sp.q.x), qg_rcp(sp.q.y));
+    const float2 T1 = qg_fma2(D, rq, qg_neg2(EmA)), T2 = qg_neg2(qg_fma2(D, rq, EmA));
     const float2 ipr = make_float2(qg_rcp(sp.pr.x), qg_rcp(sp.pr.y));
     const float2 io1 = make_float2(qg_rcp(o1.x), qg_rcp(o1.y)), io2 = make_float2(qg_rcp(o2.x), qg_rcp(o2.y));
     const float2 a2 = qg_bc(a), kT2 = qg_bc(kT);
@@ -581,7 +599,7 @@ __device__ __forceinline__ QgGrad2 qg_epilogue2(float2 E, float2 MI, float2 MJ, 
     float2 H = qg_bc(0.0f);
     if (kT != 0.0f) {
         const float2 arg = qg_mul2(qg_mul2(sp.q, o1), o2);
-        H = make_float2(const1 + logf(arg.x), const1 + logf(arg.y));
+        H = make_float2(__fadd_rn(const1, logf(arg.x)), __fadd_rn(const1, logf(arg.y)));
     }
     g.da = qg_fma2(kT2, H, E);
     g.do1 = qg_mul2(qg_mul2(a2, qg_add2(T1, kT2)), io1);
@@ -601,8 +619,8 @@ __device__ __forceinline__ QgGrad2 qg_edge2p(const QgTables &tab, int Krt, float
     QgSpectral2 sp;
     sp.set(p);
     const float2 r2 = qg_bc(sqrt2);
-    const float2 A = qg_mul2(r2, qg_sub2(qg_mul2(o1, sp.s), qg_mul2(o2, sp.t)));
-    const float2 B = qg_mul2(r2, qg_sub2(qg_mul2(o1, sp.t), qg_mul2(o2, sp.s)));
+    const float2 A = qg_mul2(r2, qg_fma2(o1, sp.s, qg_neg2(qg_mul2(o2, sp.t))));      // explicit FMAs: see qg_epilogue2
+    const float2 B = qg_mul2(r2, qg_fma2(o1, sp.t, qg_neg2(qg_mul2(o2, sp.s))));
     const float2 d0 = qg_sub2(u1, u2), eps2 = qg_bc(epsn), zero = qg_bc(0.0f);
     float2 E = zero, MI = zero, MJ = zero, MII = zero, MJJ = zero, MB = zero;
 #pragma unroll 1
@@ -638,9 +656,7 @@ __device__ __forceinline__ QgGrad2 qg_edge2p(const QgTables &tab, int Krt, float
         MB = qg_fma2(S1, qg_bc(wxr), MB);
         MJJ = qg_fma2(S0, qg_bc(wxxr), MJJ);
     }
-    const float2 sc = qg_bc(-lambdas * invpi);
-    return qg_epilogue2(qg_mul2(E, sc), qg_mul2(MI, sc), qg_mul2(MJ, sc), qg_mul2(MII, sc), qg_mul2(MJJ, sc), qg_mul2(MB, sc), sp, a,
-                        o1, o2, p, T);
+    return qg_epilogue2(E, MI, MJ, MII, MJJ, MB, qg_bc(__fmul_rn(-lambdas, invpi)), sp, a, o1, o2, p, T);
 }
 
 // Node sample for a belief whose whole quadrature cloud lies inside the image: the clamps of :157-162 cannot fire, so the

@@ -40,10 +40,11 @@ __device__ __forceinline__ float qg_warp_sum(float v) {
 
 // Block partial sums (fp32 within a warp, fp64 across warps and blocks) of red[] = {energy, dalpha, |G_muu|, |G_sigu|}; the
 // last block to finish reduces all partials in a fixed order and advances the control block (:36,:48,:50,:69-75).
-template <bool DUMP, int TH>
-__device__ __forceinline__ void qg_block_finish(const QgIterParams &p, QgCtrl *ctrl, const float (&red)[QG_NRED], int r, int j)
+// NW = warps of the CTA, W0 = first warp that owns output rows (1 when warp 0 is the halo row).
+template <bool DUMP, int NW, int W0>
+__device__ __forceinline__ void qg_block_finish_w(const QgIterParams &p, QgCtrl *ctrl, const float (&red)[QG_NRED], int r, int j)
 {
-    __shared__ double sh_red[TH + 1][QG_NRED];
+    __shared__ double sh_red[NW][QG_NRED];
     __shared__ int sh_last;
 #pragma unroll
     for (int k = 0; k < QG_NRED; ++k) {
@@ -57,7 +58,7 @@ __device__ __forceinline__ void qg_block_finish(const QgIterParams &p, QgCtrl *c
     if (tid < QG_NRED) {
         double s = 0.0;
 #pragma unroll
-        for (int w = 1; w <= TH; ++w) s += sh_red[w][tid];
+        for (int w = W0; w < NW; ++w) s += sh_red[w][tid];
         p.partials[(size_t)blk * QG_NRED + tid] = s;
     }
     if (DUMP) return;
@@ -77,7 +78,7 @@ __device__ __forceinline__ void qg_block_finish(const QgIterParams &p, QgCtrl *c
     if (!sh_last) return;
     asm volatile("fence.acq_rel.gpu;" ::: "memory");       // acquire side: every block's partials are visible after its ticket
     __shared__ double sh_sum[QG_LMAX * QG_NRED];
-    const int nthr = QG_TW * (TH + 1), warp = tid >> 5, lane = tid & 31, nwarp = nthr / 32;
+    const int nthr = QG_TW * NW, warp = tid >> 5, lane = tid & 31, nwarp = nthr / 32;
     for (int ll = 0; ll < p.L; ++ll) {
         double acc[QG_NRED] = {0.0, 0.0, 0.0, 0.0};
         const double *pp = p.partials + (size_t)ll * nblk_l * QG_NRED;
@@ -112,6 +113,12 @@ __device__ __forceinline__ void qg_block_finish(const QgIterParams &p, QgCtrl *c
     }
 }
 
+template <bool DUMP, int TH>
+__device__ __forceinline__ void qg_block_finish(const QgIterParams &p, QgCtrl *ctrl, const float (&red)[QG_NRED], int r, int j)
+{
+    qg_block_finish_w<DUMP, TH + 1, 1>(p, ctrl, red, r, j);
+}
+
 // Row band over peer memory (QgIterParams::band == 2): the updated beliefs of the band's first / last row also go straight into
 // the neighbouring band's halo row of the same ping-pong buffer (NVLink stores; qgmap_peer.cuh).  f0..f0+nf-1: fields to copy.
 __device__ __forceinline__ void qg_publish_row(const QgIterParams &p, int it, int m, int n, int l, const float *o, long long fstr,
@@ -130,7 +137,7 @@ __device__ __forceinline__ void qg_publish_row(const QgIterParams &p, int it, in
 }
 
 template <int KT, bool SUPER, bool DUMP>
-__global__ void __launch_bounds__(QG_TW *(QgTile<KT, SUPER>::TH + 1), QgTile<KT, SUPER>::MINB)
+__global__ void __launch_bounds__(QG_TW *(QgTile<KT, SUPER>::TH + QgTile<KT, SUPER>::W0), QgTile<KT, SUPER>::MINB)
 qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
 {
     QgCtrl *ctrl = p.ctrl;
@@ -140,17 +147,18 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
     const float *__restrict__ in = p.buf[(it - 1) & 1];
     float *__restrict__ out = p.buf[it & 1];
 
-    constexpr int TH = QgTile<KT, SUPER>::TH;
+    constexpr int TH = QgTile<KT, SUPER>::TH, W0 = QgTile<KT, SUPER>::W0;    // W0 = 1: warp 0 is the halo row above the tile
     const int j = threadIdx.x, r = threadIdx.y;
     const int l = blockIdx.z;
     const int n = (int)blockIdx.x * (QG_TW - 1) + j;              // global column (lane 0 = halo column n0-1)
-    const int m = p.out_r0 + qg_tile_row() * TH + r - 1;          // global row    (warp 0 = halo row m0-1)
+    const int m = p.out_r0 + qg_tile_row() * TH + r - W0;         // global row    (with a halo warp: warp 0 = row m0-1)
     const bool incol = (n >= 1) && (n <= p.N - 2);                // interior column
     const bool inrow = (m >= p.out_r0) && (m < p.out_r1);         // row this handle updates (interior by construction)
-    const bool is_out = (r >= 1) && (j >= 1) && inrow && incol;
+    const bool is_out = (r >= W0) && (j >= 1) && inrow && incol;
     // halo warp: down edge of the row above the tile; halo lane: right edge of the column left of the tile
-    const bool need_down = is_out || ((r == 0) && (j >= 1) && incol && (m + 1 < p.out_r1));
-    const bool need_right = is_out || ((j == 0) && (r >= 1) && inrow && (n + 1 <= p.N - 2));
+    const bool need_down = is_out || (W0 && (r == 0) && (j >= 1) && incol && (m + 1 < p.out_r1));
+    const bool need_right = is_out || ((j == 0) && (r >= W0) && inrow && (n + 1 <= p.N - 2));
+    const bool up_edge = !W0 && (r == 0) && is_out;               // no halo warp: the first row evaluates the down edge above it too
     const bool active = need_down || need_right;
 
     const float a = (float)ctrl->alpha[l];
@@ -170,6 +178,9 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
 
     QgGrad2 gd = {}, gr = {};
     float rou0 = 0.f, rou1 = 0.f, rou2 = 0.f, rou3 = 0.f;
+    float4 up = make_float4(0.f, 0.f, 0.f, 0.f);
+    float lf_du_u = 0.f, lf_do_u = 0.f, lf_du_v = 0.f, lf_do_v = 0.f;
+    __shared__ float4 sh_dn[TH + W0][QG_TW];
 
     // ---- down edge (m,n)->(m+1,n), layers u and v as one fp32x2 stream  (:31-34, e=1) ----------------------------------
     if (need_down) {
@@ -192,14 +203,26 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
                            p.lambdas, p.epsn, T);
     }
     // ---- endpoint-2 exchange (before the node term: the warps of a CTA then never wait for each other again until the
-    //      final block reduction, and the cheap halo warp does not stall the barrier) ---------------------------------
-    __shared__ float4 sh_dn[TH + 1][QG_TW];
+    //      final block reduction) ----------------------------------------------------------------------------------------
     sh_dn[r][j] = make_float4(gd.du2.x, gd.do2.x, gd.du2.y, gd.do2.y);          // to pixel (m+1,n)
-    const float lf_du_u = __shfl_up_sync(0xffffffffu, gr.du2.x, 1);             // from pixel (m,n-1)
-    const float lf_do_u = __shfl_up_sync(0xffffffffu, gr.do2.x, 1);
-    const float lf_du_v = __shfl_up_sync(0xffffffffu, gr.du2.y, 1);
-    const float lf_do_v = __shfl_up_sync(0xffffffffu, gr.do2.y, 1);
+    lf_du_u = __shfl_up_sync(0xffffffffu, gr.du2.x, 1);                         // from pixel (m,n-1)
+    lf_do_u = __shfl_up_sync(0xffffffffu, gr.do2.x, 1);
+    lf_du_v = __shfl_up_sync(0xffffffffu, gr.du2.y, 1);
+    lf_do_v = __shfl_up_sync(0xffffffffu, gr.do2.y, 1);
     __syncthreads();
+    // ---- tiles without a halo warp: the first row evaluates the down edge (m-1,n)->(m,n) itself, for its endpoint-2 part -- after the
+    //      barrier, so that no other row waits for it.  This is a second inlined copy of qg_edge2p; the file is compiled with
+    //      -fmad=false (csrc/Makefile) so that both copies round identically: an edge's value must not depend on which tile row
+    //      evaluates it (bit-identical results for every band split; with contraction left to ptxas the two copies differed in do2).
+    if (up_edge) {
+        const long long iup = idx - p.P;
+        const QgGrad2 gh = qg_edge2p<KT>(p.tab, p.K, a,
+                                         make_float2(qg_lds(base + F_MUU * fstr + iup), qg_lds(base + F_MUV * fstr + iup)), make_float2(muu, muv),
+                                         make_float2(qg_lds(base + F_SIGU * fstr + iup), qg_lds(base + F_SIGV * fstr + iup)), make_float2(sigu, sigv),
+                                         make_float2(qg_lds(base + F_ROU0 * fstr + iup), qg_lds(base + F_ROU2 * fstr + iup)),
+                                         p.lambdas, p.epsn, T);
+        up = make_float4(gh.du2.x, gh.do2.x, gh.du2.y, gh.do2.y);
+    }
 
     // ---- node term set-up (:87-93).  Full resolution: the bounding box of the K x K sample cloud around the mean,
     //      |x - mu| <= sqrt2 * sigma * (|s| + |t|) * X_max; inside the image for every belief of the warp -> the clamps of
@@ -229,7 +252,7 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
     if (is_out) {
         // :37-40 edge part of the assembled gradients: sum_e d1 + shifted d2 (down edge of (m-1,n), right edge of (m,n-1)).
         // Folded into 6 scalars now so that little stays live across the node quadrature.
-        const float4 up = sh_dn[r - 1][j];
+        if (W0 || r > 0) up = sh_dn[r - 1][j];
         const float E_muu = ((gd.du1.x + gr.du1.x) + up.x) + lf_du_u;
         const float E_sigu = ((gd.do1.x + gr.do1.x) + up.y) + lf_do_u;
         const float E_muv = ((gd.du1.y + gr.du1.y) + up.z) + lf_du_v;
@@ -309,7 +332,7 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
         }
     }
 
-    qg_block_finish<DUMP, TH>(p, ctrl, red, r, j);
+    qg_block_finish_w<DUMP, TH + W0, W0>(p, ctrl, red, r, j);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -319,11 +342,24 @@ qgmap_iter_kernel(const __grid_constant__ QgIterParams p)
 // are perfectly balanced) and the XJ rows r = g, g+4, ... of the node quadrature; the six node moments are combined with
 // two xor-shuffles, the edge gradients with one or two (north_star: "warp-shuffle reductions of the gradients").
 // A warp covers 8 columns (column group 0 = halo column); tile = 7 x TH outputs.
+// No halo WARP here (QG_G4_HALO_WARP = 0): a lane's node share is ~9x its edge quadrature, so the first row's down-edge lanes evaluate
+// the down edge of the row above the tile as a second quadrature (+9% on one warp of TH) instead of a warp that idles after its edges
+// (1 of 5 warp slots in the super-pixel tile; profiles/r02_iter_super_L3K5_480x640_v12_g4_it3000_ncu_full.txt: 24% of the warp samples
+// at the block-reduction barrier).  The one-thread-per-belief kernel keeps its halo warp: there the extra edge is +19% (r01 experiment 7).
 #define QG_G 4
 #define QG_CW (QG_TW / QG_G)
+#ifndef QG_G4_HALO_WARP
+#define QG_G4_HALO_WARP 0
+#endif
+#define QG_G4_W0 (QG_G4_HALO_WARP ? 1 : 0)                          // first warp that owns an output row
+template <int KT, bool SUPER> struct QgTileG4 {
+    static constexpr int TH = QgTile<KT, SUPER>::TH;
+    static constexpr int NW = TH + QG_G4_W0;                       // warps per CTA
+    static constexpr int MINB = QG_G4_HALO_WARP ? QgTile<KT, SUPER>::MINB : (SUPER ? QG_SUPER_MINB_NOHALO : QgTile<KT, SUPER>::MINB);
+};
 
 template <int KT, bool SUPER, bool DUMP>
-__global__ void __launch_bounds__(QG_TW *(QgTile<KT, SUPER>::TH + 1), QgTile<KT, SUPER>::MINB)
+__global__ void __launch_bounds__(QG_TW * QgTileG4<KT, SUPER>::NW, QgTileG4<KT, SUPER>::MINB)
 qgmap_iter_kernel_g4(const __grid_constant__ QgIterParams p)
 {
     QgCtrl *ctrl = p.ctrl;
@@ -339,12 +375,12 @@ qgmap_iter_kernel_g4(const __grid_constant__ QgIterParams p)
     const int l = blockIdx.z;
     constexpr int TH = QgTile<KT, SUPER>::TH;
     const int n = (int)blockIdx.x * (QG_CW - 1) + jc;              // global column (group 0 = halo column n0-1)
-    const int m = p.out_r0 + qg_tile_row() * TH + r - 1;           // global row    (warp 0 = halo row m0-1)
+    const int m = p.out_r0 + qg_tile_row() * TH + r - QG_G4_W0;    // global row    (with a halo warp: warp 0 = halo row m0-1)
     const bool incol = (n >= 1) && (n <= p.N - 2);
     const bool inrow = (m >= p.out_r0) && (m < p.out_r1);
-    const bool is_out = (r >= 1) && (jc >= 1) && inrow && incol;
-    const bool need_down = is_out || ((r == 0) && (jc >= 1) && incol && (m + 1 < p.out_r1));
-    const bool need_right = is_out || ((jc == 0) && (r >= 1) && inrow && (n + 1 <= p.N - 2));
+    const bool is_out = (r >= QG_G4_W0) && (jc >= 1) && inrow && incol;
+    const bool need_down = is_out || (QG_G4_HALO_WARP && (r == 0) && (jc >= 1) && incol && (m + 1 < p.out_r1));
+    const bool need_right = is_out || ((jc == 0) && (r >= QG_G4_W0) && inrow && (n + 1 <= p.N - 2));
     const bool my_edge = e ? need_right : need_down;
 
     const float a = (float)ctrl->alpha[l];
@@ -355,27 +391,44 @@ qgmap_iter_kernel_g4(const __grid_constant__ QgIterParams p)
     const long long idx = (long long)(m - p.g0) * p.P + n;
     const long long fstr = (long long)p.L * pl;
 
-    // ---- this lane's edge quadrature (:31-34) ----------------------------------------------------------------------
+    // ---- this lane's edge quadrature (:31-34).  Without a halo warp the tile's first row evaluates a second one AFTER the exchange
+    //      barrier (producer and consumer are the same thread, so the other rows do not wait for it): the down edge (m-1,n)->(m,n) of
+    //      its layer, for the endpoint-2 part.  Both run through ONE call site -- a two-trip loop with the barrier in the middle --
+    //      because two inlined copies of qg_edge may contract their FMAs differently, and an edge's value must not depend on which
+    //      tile row evaluates it (bit-identical results for every band split).
+    __shared__ float sh_dn[QgTileG4<KT, SUPER>::NW][QG_CW][4];
     QgGrad ge = {};
-    float rouq = 0.f;
-    if (my_edge) {
-        const long long inb = idx + (e ? 1 : p.P);
-        const float *mu = base + (c ? F_MUV : F_MUU) * fstr, *sg = base + (c ? F_SIGV : F_SIGU) * fstr;
-        rouq = __ldg(base + (F_ROU0 + g) * fstr + idx);
-        ge = qg_edge<KT>(p.tab, p.K, a, __ldg(mu + idx), __ldg(mu + inb), __ldg(sg + idx), __ldg(sg + inb), rouq, p.lambdas, p.epsn, T);
+    float rouq = 0.f, up_du = 0.f, up_do = 0.f, lf_du = 0.f, lf_do = 0.f;
+    const float *mu = base + (c ? F_MUV : F_MUU) * fstr, *sg = base + (c ? F_SIGV : F_SIGU) * fstr;
+    const bool up_edge = !QG_G4_HALO_WARP && (r == 0) && (e == 0) && is_out;
+#pragma unroll 1
+    for (int pass = 0; pass < (QG_G4_HALO_WARP ? 1 : 2); ++pass) {
+        const bool on = pass ? up_edge : my_edge;
+        const long long i1 = pass ? idx - p.P : idx;                             // edge origin
+        const long long i2 = pass ? idx : idx + (e ? 1 : p.P);                   // edge end point
+        QgGrad gq = {};
+        float rq = 0.f;
+        if (on) {
+            rq = __ldg(base + (F_ROU0 + g) * fstr + i1);
+            gq = qg_edge<KT>(p.tab, p.K, a, __ldg(mu + i1), __ldg(mu + i2), __ldg(sg + i1), __ldg(sg + i2), rq, p.lambdas, p.epsn, T);
+        }
+        if (pass == 0) {
+            ge = gq; rouq = rq;
+            // endpoint-2 exchange: down edges through shared memory to the row below, right edges by shuffle to the next group
+            if (e == 0) { sh_dn[r][jc][2 * c] = ge.du2; sh_dn[r][jc][2 * c + 1] = ge.do2; }
+            lf_du = __shfl_up_sync(0xffffffffu, ge.du2, QG_G);                   // lanes e==1: right edge of pixel (m,n-1), same layer
+            lf_do = __shfl_up_sync(0xffffffffu, ge.do2, QG_G);
+            __syncthreads();
+        } else { up_du = gq.du2; up_do = gq.do2; }
     }
-    // ---- endpoint-2 exchange: down edges through shared memory to the row below, right edges by shuffle to the next group
-    __shared__ float sh_dn[TH + 1][QG_CW][4];
-    if (e == 0) { sh_dn[r][jc][2 * c] = ge.du2; sh_dn[r][jc][2 * c + 1] = ge.do2; }
-    const float lf_du = __shfl_up_sync(0xffffffffu, ge.du2, QG_G);            // lanes e==1: right edge of pixel (m,n-1), same layer
-    const float lf_do = __shfl_up_sync(0xffffffffu, ge.do2, QG_G);
-    __syncthreads();
 
     // per-lane share of the folded edge gradients (:37-40): layer c of this lane
     float pm = ge.du1, ps = ge.do1;
     if (is_out) {
-        if (e == 0) { pm += sh_dn[r - 1][jc][2 * c]; ps += sh_dn[r - 1][jc][2 * c + 1]; }
-        else        { pm += lf_du; ps += lf_do; }
+        if (e == 0) {
+            if (QG_G4_HALO_WARP || r > 0) { pm += sh_dn[r - 1][jc][2 * c]; ps += sh_dn[r - 1][jc][2 * c + 1]; }
+            else                          { pm += up_du; ps += up_do; }
+        } else { pm += lf_du; ps += lf_do; }
     }
     const float E_mu = pm + __shfl_xor_sync(0xffffffffu, pm, 1);             // lanes (g, g^1) share the layer
     const float E_sig = ps + __shfl_xor_sync(0xffffffffu, ps, 1);
@@ -450,5 +503,5 @@ qgmap_iter_kernel_g4(const __grid_constant__ QgIterParams p)
             }
         }
     }
-    qg_block_finish<DUMP, TH>(p, ctrl, red, r, j);
+    qg_block_finish_w<DUMP, QgTileG4<KT, SUPER>::NW, QG_G4_W0>(p, ctrl, red, r, j);
 }
