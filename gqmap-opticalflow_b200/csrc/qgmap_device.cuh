@@ -30,6 +30,10 @@
 #ifndef QG_SMALLK_MINB
 #define QG_SMALLK_MINB 4
 #endif
+#ifndef QG_K5_TH
+#define QG_K5_TH 8          // rows (= warps) of the K=5 tile without a halo warp; QG_K5_MINB resident CTAs
+#define QG_K5_MINB QG_SMALLK_MINB
+#endif
 #ifndef QG_SUPER_TH
 #define QG_SUPER_TH 4
 #define QG_SUPER_MINB 4
@@ -41,12 +45,12 @@ __host__ __device__ constexpr int qg_template_k(int K) { return (K == 3 || K == 
 // K below: the template K (qg_template_k).  Halo warp kept for K = 3 (-2.5% without), run-time K (-4.7%) and the one-lane super-pixel form.
 __host__ __device__ constexpr int qg_tile_halo(int K, bool super) { return (QG_HALO_WARP || super || K == 3 || K == 0) ? 1 : 0; }
 __host__ __device__ constexpr int qg_tile_rows(int K, bool super) {      // rows per tile
-    return super ? QG_SUPER_TH : 8 - ((K == 3 || K == 5) ? qg_tile_halo(K, super) : 0);
+    return super ? QG_SUPER_TH : ((K == 5 && !qg_tile_halo(K, super)) ? QG_K5_TH : 8 - ((K == 3 || K == 5) ? qg_tile_halo(K, super) : 0));
 }
 template <int KT, bool SUPER> struct QgTile {
     static constexpr int W0 = qg_tile_halo(KT, SUPER);
     static constexpr int TH = qg_tile_rows(KT, SUPER);
-    static constexpr int MINB = SUPER ? QG_SUPER_MINB : ((KT > 0 && KT <= 5) ? QG_SMALLK_MINB : 3);
+    static constexpr int MINB = SUPER ? QG_SUPER_MINB : ((KT == 5 && !W0) ? QG_K5_MINB : ((KT > 0 && KT <= 5) ? QG_SMALLK_MINB : 3));
 };
 #define QG_TH_MAX 8
 #define QG_NRED 4           // block-reduced scalars: energy, dalpha, sum|G_muu|, sum|G_sigu|
