@@ -41,6 +41,16 @@ def test_small_and_ragged_grids(pkg, O, variant, shape):
     _check(pkg, O, cfg, I1, I2, st, variant)
 
 
+@pytest.mark.parametrize("K", [5, 9, 4])
+@pytest.mark.parametrize("M", [4, 5, 10, 11, 18, 19])
+def test_tile_row_boundaries(pkg, O, M, K):
+    """Heights around the tile rows of every kernel form (8 rows without a halo warp for K=5/7/9/11, where the tile's first row evaluates
+    the down edge above it itself; 8 + halo warp for run-time K; 7 + halo warp for K=3): 2 and 3 interior rows (the library needs a 4 x 4 image), exactly one tile, one
+    tile + 1 row, two tiles, two tiles + 1 row; 38 interior columns = one full 31-column tile + 7."""
+    cfg, I1, I2, st = make_problem(O, M, 40, 2, K, seed=45 + M, small_sigma=True)
+    _check(pkg, O, cfg, I1, I2, st, "full", rtol=6e-4)
+
+
 @pytest.mark.parametrize("L,K", [(10, 3), (1, 2), (2, 13), (1, 32)])
 def test_extreme_L_and_K(pkg, O, L, K):
     cfg, I1, I2, st = make_problem(O, 20, 24, L, K, seed=43, small_sigma=True)

@@ -303,3 +303,19 @@ def test_solve_outputs(pkg, O):
     for a, b in ((mu2[..., 0], ref.muu), (mu2[..., 1], ref.muv), (sigma2[..., 0], ref.sigu), (sigma2[..., 1], ref.sigv)):
         assert (np.abs(a - b) > 5e-4).mean() < 0.01 and np.abs(a - b).max() < 0.2
     assert np.allclose(alpha2.ravel(), ref.alpha, atol=1e-15)
+
+
+def test_programmatic_dependent_launch_is_bit_identical(pkg, O, monkeypatch):
+    """QGMAP_PDL=1 (iteration launches carry the programmatic-serialization attribute, the kernel waits on griddepcontrol before it reads
+    anything the previous iteration wrote) must not change a single bit, also across the 25-node CUDA graphs."""
+    cfg, I1, I2, st = make_problem(O, 60, 84, 2, 5, seed=11)
+    out = []
+    for pdl in ("0", "1"):
+        monkeypatch.setenv("QGMAP_PDL", pdl)
+        with pkg.Solver(options_from_cfg(cfg), I1, I2, variant="full") as s:
+            s.set_state(state_dict(st))
+            r = s.step(60)
+            out.append((r["Energy"].copy(), s.get_state()))
+    assert np.array_equal(out[0][0], out[1][0])
+    for k in ("muu", "muv", "sigmau", "sigmav", "pn", "rou"):
+        assert np.array_equal(out[0][1][k], out[1][1][k]), k
