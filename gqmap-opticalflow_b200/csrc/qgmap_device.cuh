@@ -496,61 +496,6 @@ __device__ __forceinline__ QgGrad qg_edge(const QgTables &tab, int Krt, float a,
     return qg_epilogue(m, sp, a, o1, o2, p, T);
 }
 
-// Two edge quadratures at once: the u- and v-layer edges of one direction share every table constant, so their samples run
-// as one fp32x2 stream (5 FFMA2 + 2 MUFU per sample pair instead of 10 FFMA + 2 MUFU).  .x = u layer, .y = v layer.
-template <int KT>
-__device__ __forceinline__ void qg_edge2(const QgTables &tab, int Krt, float a, float2 u1, float2 u2, float2 o1, float2 o2, float2 p,
-                                         float lambdas, float epsn, float T, QgGrad &gu, QgGrad &gv)
-{
-    const float sqrt2 = 1.4142135623730951f;
-    const int K = KT > 0 ? KT : Krt;
-    QgSpectral su, sv;
-    su.set(p.x);
-    sv.set(p.y);
-    const float2 A = make_float2(sqrt2 * (o1.x * su.s - o2.x * su.t), sqrt2 * (o1.y * sv.s - o2.y * sv.t));
-    const float2 B = make_float2(sqrt2 * (o1.x * su.t - o2.x * su.s), sqrt2 * (o1.y * sv.t - o2.y * sv.s));
-    const float2 d0 = qg_sub2(u1, u2), eps2 = qg_bc(epsn), zero = qg_bc(0.0f);
-    float2 E = zero, MI = zero, MJ = zero, MII = zero, MJJ = zero, MB = zero;
-#pragma unroll 1
-    for (int r = 0; r < K; ++r) {
-        const float2 dr = qg_fma2(B, qg_bc(tab.X[r]), d0);
-        float2 S0 = zero, S1 = zero, S2 = zero;
-        if (KT > 0) {
-#pragma unroll
-            for (int c = 0; c < (KT > 0 ? KT : 1); ++c) {
-                const float2 d = qg_fma2(A, qg_bc(tab.X[c]), dr);
-                const float2 q = qg_fma2(d, d, eps2);
-                const float2 f = make_float2(qg_sqrt(q.x), qg_sqrt(q.y));
-                S0 = qg_fma2(f, qg_bc(tab.W[c]), S0);
-                S1 = qg_fma2(f, qg_bc(tab.WX[c]), S1);
-                S2 = qg_fma2(f, qg_bc(tab.WXX[c]), S2);
-            }
-        } else {
-#pragma unroll 1
-            for (int c = 0; c < K; ++c) {
-                const float2 d = qg_fma2(A, qg_bc(tab.X[c]), dr);
-                const float2 q = qg_fma2(d, d, eps2);
-                const float2 f = make_float2(qg_sqrt(q.x), qg_sqrt(q.y));
-                S0 = qg_fma2(f, qg_bc(tab.W[c]), S0);
-                S1 = qg_fma2(f, qg_bc(tab.WX[c]), S1);
-                S2 = qg_fma2(f, qg_bc(tab.WXX[c]), S2);
-            }
-        }
-        const float wr = tab.W[r], wxr = tab.WX[r], wxxr = tab.WXX[r];
-        E = qg_fma2(S0, qg_bc(wr), E);
-        MI = qg_fma2(S1, qg_bc(wr), MI);
-        MII = qg_fma2(S2, qg_bc(wr), MII);
-        MJ = qg_fma2(S0, qg_bc(wxr), MJ);
-        MB = qg_fma2(S1, qg_bc(wxr), MB);
-        MJJ = qg_fma2(S0, qg_bc(wxxr), MJJ);
-    }
-    const float sc = -lambdas;
-    QgMoments mu = {E.x * sc, MI.x * sc, MJ.x * sc, MII.x * sc, MJJ.x * sc, MB.x * sc};
-    QgMoments mv = {E.y * sc, MI.y * sc, MJ.y * sc, MII.y * sc, MJJ.y * sc, MB.y * sc};
-    gu = qg_epilogue(mu, su, a, o1.x, o2.x, p.x, T);
-    gv = qg_epilogue(mv, sv, a, o1.y, o2.y, p.y, T);
-}
-
 // ---- packed epilogue: both flow layers of one edge direction at once (.x = u layer, .y = v layer); gqmap_gpu_mixture.m:137-145.
 struct QgSpectral2 {
     float2 s, t, pr, q, c1, c2;
@@ -613,7 +558,8 @@ __device__ __forceinline__ QgGrad2 qg_epilogue2(float2 Er, float2 MIr, float2 MJ
     return g;
 }
 
-// Two edge quadratures at once (u and v layer of one direction), :118-146; as qg_edge2 with the packed epilogue.
+// Two edge quadratures at once (u and v layer of one direction), :118-146: the two layers share every table constant, so their
+// samples run as one fp32x2 stream (5 FFMA2 + 2 MUFU per sample pair instead of 10 FFMA + 2 MUFU) into the packed epilogue.
 template <int KT>
 __device__ __forceinline__ QgGrad2 qg_edge2p(const QgTables &tab, int Krt, float a, float2 u1, float2 u2, float2 o1, float2 o2, float2 p,
                                              float lambdas, float epsn, float T)
