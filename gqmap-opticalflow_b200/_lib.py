@@ -52,6 +52,8 @@ SIGNATURES = {
     "qgmap_dims": (C.c_int, [C.c_void_p, _IP, _IP, _IP]),
     "qgmap_set_state": (C.c_int, [C.c_void_p] + [_DP] * 8 + [C.c_double, C.c_int]),
     "qgmap_get_state": (C.c_int, [C.c_void_p] + [_DP] * 8 + [_DP, _IP]),
+    "qgmap_set_state_f32": (C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [_DP] * 2 + [C.c_double, C.c_int]),
+    "qgmap_get_state_f32": (C.c_int, [C.c_void_p] + [C.c_void_p] * 6 + [_DP] * 2 + [_DP, _IP]),
     "qgmap_init_state": (C.c_int, [C.c_void_p, C.c_uint64]),
     "qgmap_step": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _DP, _DP, _DP, _IP, _IP]),
     "qgmap_step_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),

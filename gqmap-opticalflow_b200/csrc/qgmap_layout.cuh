@@ -6,11 +6,11 @@
 
 // ---- layout conversion kernels (MATLAB column-major fp64 at the boundary <-> private row-major planes) ------------
 // src: column-major fp64 [rows x cols x planes]; dst: row-major T planes with pitch; copies rows [r0,r1) to local rows.
-template <typename T>
-__global__ void qgmap_import_kernel(const double *__restrict__ src, int rows, int cols, int planes, T *__restrict__ dst,
+template <typename T, typename S = double>
+__global__ void qgmap_import_kernel(const S *__restrict__ src, int rows, int cols, int planes, T *__restrict__ dst,
                                     int pitch, long long plane_stride, int r0, int r1, int g0)
 {
-    __shared__ double tile[32][33];
+    __shared__ S tile[32][33];
     const int pz = blockIdx.z;
     const int rb = r0 + blockIdx.y * 32, cb = blockIdx.x * 32;
     for (int k = threadIdx.y; k < 32; k += blockDim.y) {           // coalesced along rows (column-major source)
@@ -24,16 +24,16 @@ __global__ void qgmap_import_kernel(const double *__restrict__ src, int rows, in
     }
 }
 
-template <typename T>
+template <typename T, typename D = double>
 __global__ void qgmap_export_kernel(const T *__restrict__ src, int pitch, long long plane_stride, int g0, int r0, int r1,
-                                    double *__restrict__ dst, int rows, int cols)
+                                    D *__restrict__ dst, int rows, int cols)
 {
-    __shared__ double tile[32][33];
+    __shared__ D tile[32][33];
     const int pz = blockIdx.z;
     const int rb = r0 + blockIdx.y * 32, cb = blockIdx.x * 32;
     for (int k = threadIdx.y; k < 32; k += blockDim.y) {
         int rr = rb + k, cc = cb + threadIdx.x;
-        if (rr < r1 && cc < cols) tile[k][threadIdx.x] = (double)src[(long long)pz * plane_stride + (long long)(rr - g0) * pitch + cc];
+        if (rr < r1 && cc < cols) tile[k][threadIdx.x] = (D)src[(long long)pz * plane_stride + (long long)(rr - g0) * pitch + cc];
     }
     __syncthreads();
     for (int k = threadIdx.y; k < 32; k += blockDim.y) {

@@ -232,20 +232,34 @@ class Solver:
         return {"rou": (self.M, self.N, self.L, 2, 2), "w": (self.L,)}.get(name, (self.M, self.N, self.L))
 
     def set_state(self, state, T=None, it=1, alpha=None):
-        arrs = [f64(np.asarray(state[n], dtype=np.float64).reshape(self._shape(n), order="F")) for n in STATE_FIELDS]
+        """State arrays as the reference holds them (double) -- or all six belief arrays as float32 (MATLAB `single`): the device
+        keeps fp32, so that boundary format is lossless and moves half the bytes (qgmap_set_state_f32)."""
         al = None if alpha is None else np.ascontiguousarray(np.asarray(alpha, dtype=np.float64).ravel())
-        check(lib.qgmap_set_state(self._h, *(dptr(a) for a in arrs), dptr(al),
-                                  self.cfg.temperature if T is None else float(T), int(it)), self._h)
+        Tv = self.cfg.temperature if T is None else float(T)
+        beliefs = [n for n in STATE_FIELDS if n != "w"]
+        if all(getattr(state[n], "dtype", None) == np.float32 for n in beliefs):
+            arrs = [np.asfortranarray(np.asarray(state[n], dtype=np.float32).reshape(self._shape(n), order="F")) for n in beliefs]
+            w = np.ascontiguousarray(np.asarray(state["w"], dtype=np.float64).ravel())
+            check(lib.qgmap_set_state_f32(self._h, *(C.c_void_p(a.ctypes.data) for a in arrs), dptr(w), dptr(al), Tv, int(it)), self._h)
+            return
+        arrs = [f64(np.asarray(state[n], dtype=np.float64).reshape(self._shape(n), order="F")) for n in STATE_FIELDS]
+        check(lib.qgmap_set_state(self._h, *(dptr(a) for a in arrs), dptr(al), Tv, int(it)), self._h)
 
     def init_state(self, seed=0):
         check(lib.qgmap_init_state(self._h, C.c_uint64(int(seed))), self._h)
 
-    def get_state(self):
-        out = {n: np.zeros(self._shape(n), order="F") for n in STATE_FIELDS}
+    def get_state(self, dtype=np.float64):
+        """dtype=np.float32 returns the belief arrays as the device holds them (qgmap_get_state_f32): lossless, half the bytes."""
         alpha = np.zeros(self.L)
         T = C.c_double(0)
         it = C.c_int(0)
-        check(lib.qgmap_get_state(self._h, *(dptr(out[n]) for n in STATE_FIELDS), dptr(alpha), C.byref(T), C.byref(it)), self._h)
+        if np.dtype(dtype) == np.float32:
+            out = {n: np.zeros(self._shape(n), dtype=np.float32 if n != "w" else np.float64, order="F") for n in STATE_FIELDS}
+            check(lib.qgmap_get_state_f32(self._h, *(C.c_void_p(out[n].ctypes.data) for n in STATE_FIELDS if n != "w"), dptr(out["w"]),
+                                          dptr(alpha), C.byref(T), C.byref(it)), self._h)
+        else:
+            out = {n: np.zeros(self._shape(n), order="F") for n in STATE_FIELDS}
+            check(lib.qgmap_get_state(self._h, *(dptr(out[n]) for n in STATE_FIELDS), dptr(alpha), C.byref(T), C.byref(it)), self._h)
         out["alpha"], out["T"], out["it"] = alpha, T.value, it.value
         return out
 

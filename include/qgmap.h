@@ -98,6 +98,13 @@ int qgmap_set_state(qgmap_handle *h, const double *muu, const double *muv, const
                     const double *pn, const double *rou, const double *w, const double *alpha, double T, int it);
 int qgmap_get_state(qgmap_handle *h, double *muu, double *muv, double *sigu, double *sigv,
                     double *pn, double *rou, double *w, double *alpha, double *T, int *it);
+/* The same with single-precision belief arrays (MATLAB `single`; w, alpha, T stay double).  The device keeps the beliefs in fp32, so
+ * this boundary format is lossless -- get_state_f32 -> set_state_f32 restores the state bit for bit -- at half the host<->device
+ * bytes (2160 x 3840, L=3: 0.9 GB instead of 1.8 GB per direction), which is what a short call on a large frame pays for. */
+int qgmap_set_state_f32(qgmap_handle *h, const float *muu, const float *muv, const float *sigu, const float *sigv,
+                        const float *pn, const float *rou, const double *w, const double *alpha, double T, int it);
+int qgmap_get_state_f32(qgmap_handle *h, float *muu, float *muv, float *sigu, float *sigv,
+                        float *pn, float *rou, double *w, double *alpha, double *T, int *it);
 /* Random init exactly as :18-24 (uniform draws; generator = splitmix64-seeded xoshiro256**, not MATLAB's). */
 int qgmap_init_state(qgmap_handle *h, uint64_t seed);
 

@@ -319,3 +319,31 @@ def test_programmatic_dependent_launch_is_bit_identical(pkg, O, monkeypatch):
     assert np.array_equal(out[0][0], out[1][0])
     for k in ("muu", "muv", "sigmau", "sigmav", "pn", "rou"):
         assert np.array_equal(out[0][1][k], out[1][1][k]), k
+
+
+def test_single_precision_state_boundary(pkg, O):
+    """qgmap_set_state_f32 / qgmap_get_state_f32 (MATLAB `single` arrays at the boundary): the device keeps the beliefs in fp32, so the
+    format is lossless -- same trajectory as the double-precision boundary from fp32-representable values, get == get.astype(float32),
+    and get_state_f32 -> set_state_f32 restores the state bit for bit."""
+    cfg, I1, I2, st = make_problem(O, 44, 60, 2, 5, seed=13)
+    sd = state_dict(_round_state(st))
+    fields = ("muu", "muv", "sigmau", "sigmav", "pn", "rou")
+    with pkg.Solver(options_from_cfg(cfg), I1, I2, variant="full") as s:
+        s.set_state(sd)
+        r64 = s.step(5)
+        a, a32 = s.get_state(), s.get_state(np.float32)
+        for k in fields:
+            assert a32[k].dtype == np.float32 and a32[k].shape == a[k].shape
+            assert np.array_equal(a32[k].astype(np.float64), a[k]), k
+        assert a32["it"] == a["it"] and np.array_equal(a32["alpha"], a["alpha"]) and np.array_equal(a32["w"], a["w"])
+        s.set_state({k: (np.asarray(v, dtype=np.float32) if k != "w" else v) for k, v in sd.items()})
+        r32 = s.step(5)
+        b = s.get_state()
+        assert np.array_equal(r64["Energy"], r32["Energy"])
+        for k in fields:
+            assert np.array_equal(a[k], b[k]), k
+        s.set_state(a32, T=a32["T"], it=a32["it"], alpha=a32["alpha"])       # checkpoint / resume through the fp32 boundary
+        c = s.get_state(np.float32)
+        for k in fields:
+            assert np.array_equal(a32[k], c[k]), k
+        assert c["it"] == a32["it"]
