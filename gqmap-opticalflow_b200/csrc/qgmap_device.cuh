@@ -30,6 +30,9 @@
 #ifndef QG_SMALLK_MINB
 #define QG_SMALLK_MINB 4
 #endif
+#ifndef QG_BIGK_TH
+#define QG_BIGK_TH 8        // rows (= warps) of the K >= 7 tile without a halo warp, 3 resident CTAs
+#endif
 #ifndef QG_K5_TH
 #define QG_K5_TH 8          // rows (= warps) of the K=5 tile without a halo warp; QG_K5_MINB resident CTAs
 #define QG_K5_MINB QG_SMALLK_MINB
@@ -45,7 +48,8 @@ __host__ __device__ constexpr int qg_template_k(int K) { return (K == 3 || K == 
 // K below: the template K (qg_template_k).  Halo warp kept for K = 3 (-2.5% without), run-time K (-4.7%) and the one-lane super-pixel form.
 __host__ __device__ constexpr int qg_tile_halo(int K, bool super) { return (QG_HALO_WARP || super || K == 3 || K == 0) ? 1 : 0; }
 __host__ __device__ constexpr int qg_tile_rows(int K, bool super) {      // rows per tile
-    return super ? QG_SUPER_TH : ((K == 5 && !qg_tile_halo(K, super)) ? QG_K5_TH : 8 - ((K == 3 || K == 5) ? qg_tile_halo(K, super) : 0));
+    return super ? QG_SUPER_TH : ((K == 5 && !qg_tile_halo(K, super)) ? QG_K5_TH :
+                                  ((K >= 7 && !qg_tile_halo(K, super)) ? QG_BIGK_TH : 8 - ((K == 3 || K == 5) ? qg_tile_halo(K, super) : 0)));
 }
 template <int KT, bool SUPER> struct QgTile {
     static constexpr int W0 = qg_tile_halo(KT, SUPER);
