@@ -184,6 +184,89 @@ def run_rubberwhale_full():
     return out
 
 
+def _middlebury_step(seq, solver, L, K, consts, seed, stride, window=None, keep_truth=False, its=1):
+    """`its` iterations of `solver` (.m source, executed) on the MATLAB-rgb2gray frames of a shipped sequence, or on a window
+    (r0, r1, c0, c1) of it with the clamp range of the WHOLE sequence (what the driver computes, optical_flow.m:12-13).  Stores the
+    grey frames (uint8) so that a box without the reference tree can repeat the step, probes of the state at the solver's own
+    fprintf, and the ground truth of a window (float32, as in the .flo file) when asked."""
+    from PIL import Image
+    from oracle.mlab.minimat import Interp
+    from oracle.refbin import refbin
+    d = os.path.join(REF, "middlebury", seq)
+
+    def grey(fn):                                                            # MATLAB rgb2gray on uint8: weighted sum, rounded
+        rgb = np.asarray(Image.open(os.path.join(d, fn)).convert("RGB")).astype(np.float64)
+        return np.floor(rgb[..., 0] * 0.298936021293775 + rgb[..., 1] * 0.587043074451121 + rgb[..., 2] * 0.114020904255103 + 0.5).astype(np.uint8)
+    g1, g2 = grey("frame10.png"), grey("frame11.png")
+    Mo, No = g1.shape
+    with open(os.path.join(d, "flow10.flo"), "rb") as f:
+        f.read(12)
+        gt = np.fromfile(f, np.float32).reshape(Mo, No, 2).astype(np.float64)
+    _, tflow, minu, maxu, minv, maxv, unk = refbin.flowToColor_mex(np.asfortranarray(gt))                      # optical_flow.m:12-13, the binary
+    if window:
+        r0, r1, c0, c1 = window
+        g1, g2 = g1[r0:r1, c0:c1], g2[r0:r1, c0:c1]
+        tflow, unk = np.asfortranarray(tflow[r0:r1, c0:c1]), np.asfortranarray(np.asarray(unk)[r0:r1, c0:c1])
+        Mo, No = g1.shape
+    sup = solver == "gqmap_gpuSuper_mix_entropy"
+    M, N = (Mo // 4, No // 4) if sup else (Mo, No)
+    I1, I2 = np.asfortranarray(g1.astype(np.float64)), np.asfortranarray(g2.astype(np.float64))
+    opts = dict(trueFlow=tflow, unknownIdx=unk, its=float(its), K=float(K), L=float(L), epsn=0.001 ** 2, lambdad=1.0,
+                minu=minu, maxu=maxu, minv=minv, maxv=maxv, dir="/nonexistent", **consts)
+    rng = np.random.default_rng(seed)
+    draws = [rng.random(n).reshape(shp, order="F") for n, shp in ((L, (1, 1, L)),) + ((M * N * L, (M, N, L)),) * 4]   # :18-22
+    queue, snaps = list(draws), {}
+
+    def rand(shape):
+        a = queue.pop(0)
+        assert a.size == int(np.prod(shape))
+        return a.reshape(shape, order="F")
+
+    def probe(ws):
+        dd = {f: np.asarray(ws[f], dtype=np.float64) for f in ("muu", "muv", "sigmau", "sigmav", "pn", "rou")}
+        snaps[int(ws["it"])] = dict(ptdmu=float(ws["ptdmu"]), ptdsigma=float(ws["ptdsigma"]), T=float(ws["T"]),
+                                    sums=np.array([dd[f].sum() for f in dd] + [(dd[f] ** 2).sum() for f in dd]),
+                                    **{f: np.array(dd[f][::stride, ::stride]) for f in dd})
+    interp = Interp([REF], rand=rand, on_fprintf=probe,
+                    externals={"get_map_mex": lambda n, *a: (refbin.get_map_mex(*a),),
+                               "flowToColor_mex": lambda n, *a: refbin.flowToColor_mex(*a)[:max(n, 1)]})
+    mu, sigma, alpha, AEPE, Energy, logP = interp.call(solver, opts, I1, I2, nargout=6)
+    assert not queue
+    out = dict(I1=g1, I2=g2, range=np.array([minu, maxu, minv, maxv]), AEPE=np.ravel(AEPE), Energy=np.ravel(Energy), logP=np.ravel(logP),
+               alpha=np.ravel(alpha), seed=np.array(seed), draws_checksum=np.array([x.sum() for x in draws]))
+    if keep_truth:
+        out.update(tflow=np.asarray(tflow, dtype=np.float32), unknown=np.asarray(unk, dtype=bool))
+    for it, snap in snaps.items():
+        out.update({"p%d_%s" % (it, k): np.asarray(v) for k, v in snap.items()})
+    return out
+
+
+# Executed-source cases on the reference's OWN data (rgb2gray of the shipped PNGs, ground truth of the shipped .flo files):
+# name -> (sequence, solver file, L, K, driver constants, seed, probe stride, window (r0, r1, c0, c1) or None, keep ground truth, its)
+FULL_C = dict(temperature=0.0, drate=0.5, lambdas=5.0)                      # optical_flow.m:16-23
+SUPER_C = dict(temperature=0.2, drate=0.75, lambdas=16.0)                   # optical_flowSuper.m:16-23
+REAL_CASES = {
+    # BASELINE configs[2] at FULL size: the whole 480 x 640 Urban2 pair, 120 x 160 x 3 beliefs, 400 node_pot calls each (~80 minutes)
+    "urban2_super_full_L3K5": ("Urban2", "gqmap_gpuSuper_mix_entropy", 3, 5, SUPER_C, 2020, 4, None, False, 1),
+    # the metric's own instantiation (BASELINE configs[3]/[4]: full resolution, L=3, K=5), two iterations (~25 minutes)
+    "grove2_window_L3K5": ("Grove2", "gqmap_gpu_mixture", 3, 5, FULL_C, 2021, 4, (176, 304, 240, 400), True, 2),
+    # BASELINE configs[1] (the eight ground-truth sequences, L=2, driver default K=9): a window of Dimetrodon (~20 minutes)
+    "dimetrodon_window_L2K9": ("Dimetrodon", "gqmap_gpu_mixture", 2, 9, FULL_C, 2024, 4, (150, 246, 200, 328), True, 1),
+    # optical_flow.m AS SHIPPED: Teddy, K=9, L=3; u range [-52.75, 0], v range [0, 0] (sigma_u starts at 53 px: most samples clamp)
+    "teddy_window_L3K9": ("Teddy", "gqmap_gpu_mixture", 3, 9, FULL_C, 2022, 4, (120, 216, 160, 288), True, 1),
+    # optical_flowSuper.m AS SHIPPED: Venus, K=11, L=3, super-pixel variant; v range [0, 0]
+    "venus_super_window_L3K11": ("Venus", "gqmap_gpuSuper_mix_entropy", 3, 11, SUPER_C, 2023, 2, (100, 228, 120, 280), True, 1),
+}
+
+
+def run_real(name, crop=None):
+    """crop = (rows, cols): dry runs of the full-size case."""
+    seq, solver, L, K, consts, seed, stride, window, keep, its = REAL_CASES[name]
+    if crop:
+        window = (0, crop[0], 0, crop[1])
+    return _middlebury_step(seq, solver, L, K, consts, seed, stride, window=window, keep_truth=keep, its=its)
+
+
 def run_host_io():
     """The host-side .m files of the drivers' path, executed: readFlowFile.m, legacy/writeFlowFile.m and legacy/flowToColor.m +
     legacy/computeColor.m with the optional maxFlow argument (the compiled flowToColor_mex takes none)."""
@@ -225,7 +308,14 @@ if __name__ == "__main__":
         print("rubberwhale_full %6.1f s  Energy(1)=%.9e AEPE(1)=%.6f logP(1)=%.6e -> %d KiB" % (
             time.time() - t, out["Energy"][0], out["AEPE"][0], out["logP"][0],
             os.path.getsize(os.path.join(HERE, "refsrc_rubberwhale_full_L1K3.npz")) // 1024), flush=True)
-    for name in ([a for a in sys.argv[1:] if a not in ("host_io", "rubberwhale", "rubberwhale_full")] or ([] if sys.argv[1:] else CASES)):
+    for name in [a for a in sys.argv[1:] if a in REAL_CASES]:               # 20-80 minutes each: only on request
+        t = time.time()
+        out = run_real(name)
+        path = os.path.join(HERE, "refsrc_%s.npz" % name)
+        np.savez_compressed(path, **out)
+        print("%s %6.1f s  Energy=%s AEPE(1)=%.6f logP(1)=%.6e -> %d KiB" % (name, time.time() - t, out["Energy"], out["AEPE"][0], out["logP"][0],
+                                                                              os.path.getsize(path) // 1024), flush=True)
+    for name in ([a for a in sys.argv[1:] if a not in ("host_io", "rubberwhale", "rubberwhale_full") and a not in REAL_CASES] or ([] if sys.argv[1:] else CASES)):
         t = time.time()
         out = run_case(name)
         path = os.path.join(HERE, "refsrc_%s.npz" % name)

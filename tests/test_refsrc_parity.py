@@ -282,6 +282,127 @@ def test_cuda_step_against_executed_source_on_full_rubberwhale(pkg, O):
         assert err.max() < 5e-4 and np.median(err) < 2e-6, (f, float(err.max()), float(np.median(err)))
 
 
+# ---- executed-source cases on the reference's OWN data (tests/golden/make_refsrc_golden.py::REAL_CASES) -----------------------------
+# name -> (super-pixel variant, L, K, lambdas, T, drate, frame shape, probe stride, iterations); frames = MATLAB rgb2gray of the shipped
+# PNGs (integer grey levels: what the CUDA path gathers from its fp16 one-sector layout while the beliefs are wide), ground truth
+# and clamp range from the shipped .flo files through the reference's flowToColor_mex binary
+REAL = {
+    # the metric's own instantiation (BASELINE configs[3]/[4]: full resolution, L=3, K=5): a window of Grove2, optical_flow.m:16-23
+    "grove2_window_L3K5": (False, 3, 5, 5.0, 0.0, 0.5, (128, 160), 4, 2),
+    # BASELINE configs[1] (the eight ground-truth sequences, L=2, driver default K=9): a window of Dimetrodon
+    "dimetrodon_window_L2K9": (False, 2, 9, 5.0, 0.0, 0.5, (96, 128), 4, 1),
+}
+REAL_FILE = {name: os.path.join(GOLD, "refsrc_%s.npz" % name) for name in REAL}
+_REAL_FIELDS = (("muu", "muu"), ("muv", "muv"), ("sigu", "sigmau"), ("sigv", "sigmav"), ("pn", "pn"), ("rou", "rou"))
+
+
+def _real_case(O, name):
+    sup, L, K, lambdas, T, drate, shape, stride, its = REAL[name]
+    d = np.load(REAL_FILE[name])
+    I1, I2 = np.asfortranarray(d["I1"].astype(np.float64)), np.asfortranarray(d["I2"].astype(np.float64))
+    Mo, No = I1.shape
+    M, N = (Mo // 4, No // 4) if sup else (Mo, No)
+    rng = np.random.default_rng(int(d["seed"]))
+    draws = [rng.random(n).reshape(shp, order="F") for n, shp in ((L, (1, 1, L)),) + ((M * N * L, (M, N, L)),) * 4]
+    assert np.array_equal(np.array([x.sum() for x in draws]), d["draws_checksum"])
+    minu, maxu, minv, maxv = (float(x) for x in d["range"])
+    cfg = O.make_config(Mo, No, L, K, super=sup, lambdas=lambdas, epsn=0.001 ** 2, minu=minu, maxu=maxu, minv=minv, maxv=maxv, drate=drate)
+    w, ru, rv, su, sv = draws
+    shp = (M, N, L)
+    st = O.State(minu + ru * (maxu - minu), minv + rv * (maxv - minv), su + (maxu - minu), sv + (maxv - minv), np.zeros(shp),
+                 np.zeros(shp + (2, 2)), np.ravel(w), T=T)                      # gqmap_gpu_mixture.m:18-24
+    return d, cfg, I1, I2, st
+
+
+def _real_truth(O, name, d, shape):
+    """Ground truth of the case: stored for windows; for the whole Urban2 pair read from the reference tree where it exists."""
+    if "tflow" in d.files:
+        return np.asfortranarray(d["tflow"].astype(np.float64)), d["unknown"]
+    gt = "/root/reference/middlebury/Urban2/flow10.flo"
+    if not os.path.exists(gt):
+        return None, None
+    with open(gt, "rb") as f:
+        f.read(12)
+        flo = np.fromfile(f, np.float32).reshape(480, 640, 2).astype(np.float64)
+    r = O.flow_to_color(np.asfortranarray(flo))
+    assert tuple(float(x) for x in r[2:6]) == tuple(d["range"])
+    return np.asfortranarray(r[1][:shape[0], :shape[1]]), np.asarray(r[6])[:shape[0], :shape[1]]
+
+
+@pytest.mark.parametrize("name", sorted(REAL))
+def test_oracle_reproduces_executed_source_on_reference_data(O, name):
+    sup, L, K, lambdas, T, drate, shape, stride, its = REAL[name]
+    d, cfg, I1, I2, st = _real_case(O, name)
+    VV = O.get_vv(I2)
+    assert np.abs(st.alpha - d["alpha"]).max() < 1e-15                        # it <= 500: alpha is still softmax(w) of the draw
+    for it in range(1, its + 1):
+        tolE, tolS = (1e-13, 1e-10) if it == 1 else (1e-11, 1e-8)              # free-running: iteration 2 inherits the rounding of iteration 1
+        n, _, stopped, E, dm, ds = O.run(cfg, I1, VV, st, it, 10 ** 6, 1)
+        assert n == 1 and abs(E[0] / d["Energy"][it - 1] - 1) < tolE, (it, E[0], d["Energy"][it - 1])
+        assert abs(dm[0] / float(d["p%d_ptdmu" % it]) - 1) < 1e3 * tolE and abs(ds[0] / float(d["p%d_ptdsigma" % it]) - 1) < 1e3 * tolE
+        assert st.T == float(d["p%d_T" % it]) == T
+        for f, fname in _REAL_FIELDS:
+            ref = d["p%d_%s" % (it, fname)]
+            _close(getattr(st, f)[::stride, ::stride].reshape(ref.shape), ref, tolS, (it, f))
+        sums = np.array([getattr(st, f).sum() for f, _ in _REAL_FIELDS] + [(getattr(st, f) ** 2).sum() for f, _ in _REAL_FIELDS])
+        ok = np.abs(d["p%d_sums" % it]) > 0
+        assert np.abs(sums[ok] / d["p%d_sums" % it][ok] - 1).max() < 1e2 * tolS
+        if it == 1:
+            # monitoring at it == 1 (:52-67): get_map_mex (the reference's binary when the file was made; super: repelem(map,4,4) and
+            # the 5:end-4 crop), AEPE against the shipped ground truth, profile_logP.  The state agrees to ~1e-13 here; fminbnd's
+            # TolX = 1e-4 path and sums of both signs leave 1e-12 .. 1e-11 in the scalars.
+            mp = O.find_map(st.alpha, st.muu, st.sigu, st.muv, st.sigv)
+            assert abs(O.profile_logp(cfg, I1, VV, mp) / d["logP"][0] - 1) < 1e-10
+            tflow, unk = _real_truth(O, name, d, I1.shape)
+            if tflow is not None:
+                assert abs(O.aepe(cfg, mp, tflow, unk) / d["AEPE"][0] - 1) < 1e-10
+    assert np.all(np.isnan(d["AEPE"][1:])) and np.all(np.isnan(d["logP"][1:]))
+    assert I1.shape == shape and np.array_equal(I1, np.round(I1)) and 0 <= I1.min() and I1.max() <= 255     # the size claimed; grey levels
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(REAL))
+def test_cuda_steps_against_executed_source_on_reference_data(pkg, O, name):
+    from test_gpu_parity import _round_state
+    from test_gpu_full_size import _assert_step_close
+    sup, L, K, lambdas, T, drate, shape, stride, its = REAL[name]
+    d, cfg, I1, I2, st = _real_case(O, name)
+    VV = O.get_vv(I2)
+    tflow, unk = _real_truth(O, name, d, I1.shape)
+    before = _round_state(st)
+    ref = before.copy()
+    O.run(cfg, I1, VV, ref, 1, 10 ** 6, 1)                                     # the oracle from the fp32-rounded start, whole state
+    mp_ref = O.find_map(ref.alpha, ref.muu, ref.sigu, ref.muv, ref.sigv)
+    with pkg.Solver(options_from_cfg(cfg, T=T), I1, I2, variant="super" if sup else "full") as s:
+        s.set_state(state_dict(before), T=T, it=1, alpha=before.alpha)
+        r = s.step(1)
+        got = s.get_state()
+        own = s.map()
+        lp_own, lp_on_ref = s.logp(own), s.logp(mp_ref)
+        ae_own = s.aepe(own, tflow, unk) if tflow is not None else None
+        r2 = s.step(1) if its > 1 else None                                    # free-running second iteration
+    print("%s: Energy rel %.2e, ptdmu rel %.2e, ptdsigma rel %.2e, logP(own map) rel %.2e, AEPE diff %s" % (
+        name, r["Energy"][0] / d["Energy"][0] - 1, r["ptdmu"][0] / float(d["p1_ptdmu"]) - 1, r["ptdsigma"][0] / float(d["p1_ptdsigma"]) - 1,
+        lp_own / d["logP"][0] - 1, None if ae_own is None else "%.2e" % (ae_own - d["AEPE"][0])))
+    assert abs(r["Energy"][0] / d["Energy"][0] - 1) < 1e-5, (r["Energy"][0], d["Energy"][0])                 # north_star: 1e-4
+    # mean|G| (:69-70): 1e-4 relative plus the fp32 floor of tests/test_gpu_full_size.py (x16 pixels per super-pixel block)
+    floor_u = 3e-5 * (16 if sup else 1) * float(np.mean(1.0 / before.sigu[1:-1, 1:-1]))
+    assert abs(r["ptdmu"][0] - float(d["p1_ptdmu"])) < 1e-4 * float(d["p1_ptdmu"]) + floor_u
+    assert abs(r["ptdsigma"][0] - float(d["p1_ptdsigma"])) < 1e-4 * float(d["p1_ptdsigma"]) + floor_u
+    assert abs(lp_on_ref / O.profile_logp(cfg, I1, VV, mp_ref) - 1) < 1e-12   # the logP kernel on the oracle's map
+    assert abs(lp_own / d["logP"][0] - 1) < 1e-4                               # the CUDA path's own MAP of its own fp32 state
+    if ae_own is not None:
+        assert abs(ae_own - d["AEPE"][0]) < 1e-3                               # north_star: EPE within 1e-3 px
+    _assert_step_close(got, ref, before, cfg.step0 / (1 + 1 / cfg.step_tau), where=name)
+    for f in ("muu", "muv", "sigmau", "sigmav"):                                # and against the executed source itself, on its probes
+        pr = d["p1_" + f]
+        err = np.abs(got[f][::stride, ::stride].reshape(pr.shape) - pr)
+        assert err.max() < 5e-4 and np.median(err) < 2e-6, (f, float(err.max()), float(np.median(err)))
+    if r2 is not None:
+        assert abs(r2["Energy"][0] / d["Energy"][1] - 1) < 1e-4, (r2["Energy"][0], d["Energy"][1])
+        assert abs(r2["ptdmu"][0] / float(d["p2_ptdmu"]) - 1) < 1e-3
+
+
 # ---- host-side files of the drivers' path: readFlowFile.m, legacy/writeFlowFile.m, legacy/flowToColor.m (+ maxFlow) -----------
 def test_host_io_against_executed_source(pkg, O, tmp_path):
     d = np.load(os.path.join(GOLD, "refsrc_host_io.npz"))
