@@ -291,6 +291,10 @@ REAL = {
     "grove2_window_L3K5": (False, 3, 5, 5.0, 0.0, 0.5, (128, 160), 4, 2),
     # BASELINE configs[1] (the eight ground-truth sequences, L=2, driver default K=9): a window of Dimetrodon
     "dimetrodon_window_L2K9": (False, 2, 9, 5.0, 0.0, 0.5, (96, 128), 4, 1),
+    # optical_flow.m AS SHIPPED (Teddy, K=9, L=3): u range [-52.75, 0], v range [0, 0]
+    "teddy_window_L3K9": (False, 3, 9, 5.0, 0.0, 0.5, (96, 128), 4, 1),
+    # optical_flowSuper.m AS SHIPPED (Venus, K=11, L=3, super-pixel variant): v range [0, 0]
+    "venus_super_window_L3K11": (True, 3, 11, 16.0, 0.2, 0.75, (128, 160), 2, 1),
 }
 REAL_FILE = {name: os.path.join(GOLD, "refsrc_%s.npz" % name) for name in REAL}
 _REAL_FIELDS = (("muu", "muu"), ("muv", "muv"), ("sigu", "sigmau"), ("sigv", "sigmav"), ("pn", "pn"), ("rou", "rou"))
