@@ -287,6 +287,8 @@ def test_cuda_step_against_executed_source_on_full_rubberwhale(pkg, O):
 # PNGs (integer grey levels: what the CUDA path gathers from its fp16 one-sector layout while the beliefs are wide), ground truth
 # and clamp range from the shipped .flo files through the reference's flowToColor_mex binary
 REAL = {
+    # BASELINE configs[2] at FULL size: the whole 480 x 640 Urban2 pair, super-pixel variant, constants of optical_flowSuper.m:16-23
+    "urban2_super_full_L3K5": (True, 3, 5, 16.0, 0.2, 0.75, (480, 640), 4, 1),
     # the metric's own instantiation (BASELINE configs[3]/[4]: full resolution, L=3, K=5): a window of Grove2, optical_flow.m:16-23
     "grove2_window_L3K5": (False, 3, 5, 5.0, 0.0, 0.5, (128, 160), 4, 2),
     # BASELINE configs[1] (the eight ground-truth sequences, L=2, driver default K=9): a window of Dimetrodon
