@@ -184,11 +184,12 @@ def run_rubberwhale_full():
     return out
 
 
-def _middlebury_step(seq, solver, L, K, consts, seed, stride, window=None, keep_truth=False, its=1):
+def _middlebury_step(seq, solver, L, K, consts, seed, stride, window=None, keep_truth=False, its=1, full_at=()):
     """`its` iterations of `solver` (.m source, executed) on the MATLAB-rgb2gray frames of a shipped sequence, or on a window
     (r0, r1, c0, c1) of it with the clamp range of the WHOLE sequence (what the driver computes, optical_flow.m:12-13).  Stores the
     grey frames (uint8) so that a box without the reference tree can repeat the step, probes of the state at the solver's own
-    fprintf, and the ground truth of a window (float32, as in the .flo file) when asked."""
+    fprintf (strided; the WHOLE state, incl. alpha and w, at the iterations in full_at: keys f<it>_<field>), and the ground truth of a
+    window (float32, as in the .flo file) when asked."""
     from PIL import Image
     from oracle.mlab.minimat import Interp
     from oracle.refbin import refbin
@@ -215,7 +216,7 @@ def _middlebury_step(seq, solver, L, K, consts, seed, stride, window=None, keep_
                 minu=minu, maxu=maxu, minv=minv, maxv=maxv, dir="/nonexistent", **consts)
     rng = np.random.default_rng(seed)
     draws = [rng.random(n).reshape(shp, order="F") for n, shp in ((L, (1, 1, L)),) + ((M * N * L, (M, N, L)),) * 4]   # :18-22
-    queue, snaps = list(draws), {}
+    queue, snaps, fulls = list(draws), {}, {}
 
     def rand(shape):
         a = queue.pop(0)
@@ -224,9 +225,13 @@ def _middlebury_step(seq, solver, L, K, consts, seed, stride, window=None, keep_
 
     def probe(ws):
         dd = {f: np.asarray(ws[f], dtype=np.float64) for f in ("muu", "muv", "sigmau", "sigmav", "pn", "rou")}
-        snaps[int(ws["it"])] = dict(ptdmu=float(ws["ptdmu"]), ptdsigma=float(ws["ptdsigma"]), T=float(ws["T"]),
-                                    sums=np.array([dd[f].sum() for f in dd] + [(dd[f] ** 2).sum() for f in dd]),
-                                    **{f: np.array(dd[f][::stride, ::stride]) for f in dd})
+        it = int(ws["it"])
+        snaps[it] = dict(ptdmu=float(ws["ptdmu"]), ptdsigma=float(ws["ptdsigma"]), T=float(ws["T"]),
+                         sums=np.array([dd[f].sum() for f in dd] + [(dd[f] ** 2).sum() for f in dd]),
+                         **{f: np.array(dd[f][::stride, ::stride]) for f in dd})
+        if it in full_at:
+            fulls[it] = dict({f: np.array(dd[f], order="F") for f in dd}, alpha=np.ravel(np.asarray(ws["alpha"], dtype=np.float64)).copy(),
+                             w=np.ravel(np.asarray(ws["w"], dtype=np.float64)).copy())
     interp = Interp([REF], rand=rand, on_fprintf=probe,
                     externals={"get_map_mex": lambda n, *a: (refbin.get_map_mex(*a),),
                                "flowToColor_mex": lambda n, *a: refbin.flowToColor_mex(*a)[:max(n, 1)]})
@@ -238,6 +243,8 @@ def _middlebury_step(seq, solver, L, K, consts, seed, stride, window=None, keep_
         out.update(tflow=np.asarray(tflow, dtype=np.float32), unknown=np.asarray(unk, dtype=bool))
     for it, snap in snaps.items():
         out.update({"p%d_%s" % (it, k): np.asarray(v) for k, v in snap.items()})
+    for it, full in fulls.items():
+        out.update({"f%d_%s" % (it, k): np.asarray(v) for k, v in full.items()})
     return out
 
 
@@ -259,8 +266,16 @@ REAL_CASES = {
 }
 
 
+# A longer run, for single steps from LATER states of the reference's own trajectory on its own data (at iteration 1 every correlation is
+# still zero): a 48 x 64 window of Grove2, L=3, K=5, 16 iterations, the whole state kept after iterations 15 and 16 (~30 minutes)
+REAL_LONG = {"grove2_window_L3K5_it16": ("Grove2", "gqmap_gpu_mixture", 3, 5, FULL_C, 2025, 4, (208, 256, 280, 344), True, 16, (15, 16))}
+
+
 def run_real(name, crop=None):
     """crop = (rows, cols): dry runs of the full-size case."""
+    if name in REAL_LONG:
+        seq, solver, L, K, consts, seed, stride, window, keep, its, full_at = REAL_LONG[name]
+        return _middlebury_step(seq, solver, L, K, consts, seed, stride, window=window, keep_truth=keep, its=its, full_at=full_at)
     seq, solver, L, K, consts, seed, stride, window, keep, its = REAL_CASES[name]
     if crop:
         window = (0, crop[0], 0, crop[1])
@@ -308,14 +323,14 @@ if __name__ == "__main__":
         print("rubberwhale_full %6.1f s  Energy(1)=%.9e AEPE(1)=%.6f logP(1)=%.6e -> %d KiB" % (
             time.time() - t, out["Energy"][0], out["AEPE"][0], out["logP"][0],
             os.path.getsize(os.path.join(HERE, "refsrc_rubberwhale_full_L1K3.npz")) // 1024), flush=True)
-    for name in [a for a in sys.argv[1:] if a in REAL_CASES]:               # 20-80 minutes each: only on request
+    for name in [a for a in sys.argv[1:] if a in REAL_CASES or a in REAL_LONG]:               # 20-80 minutes each: only on request
         t = time.time()
         out = run_real(name)
         path = os.path.join(HERE, "refsrc_%s.npz" % name)
         np.savez_compressed(path, **out)
         print("%s %6.1f s  Energy=%s AEPE(1)=%.6f logP(1)=%.6e -> %d KiB" % (name, time.time() - t, out["Energy"], out["AEPE"][0], out["logP"][0],
                                                                               os.path.getsize(path) // 1024), flush=True)
-    for name in ([a for a in sys.argv[1:] if a not in ("host_io", "rubberwhale", "rubberwhale_full") and a not in REAL_CASES] or ([] if sys.argv[1:] else CASES)):
+    for name in ([a for a in sys.argv[1:] if a not in ("host_io", "rubberwhale", "rubberwhale_full") and a not in REAL_CASES and a not in REAL_LONG] or ([] if sys.argv[1:] else CASES)):
         t = time.time()
         out = run_case(name)
         path = os.path.join(HERE, "refsrc_%s.npz" % name)

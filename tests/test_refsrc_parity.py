@@ -409,6 +409,66 @@ def test_cuda_steps_against_executed_source_on_reference_data(pkg, O, name):
         assert abs(r2["ptdmu"][0] / float(d["p2_ptdmu"]) - 1) < 1e-3
 
 
+# ---- single steps from LATER states of the reference's own trajectory on its own data (at iteration 1 every correlation is still zero) ----
+# tests/golden/make_refsrc_golden.py::REAL_LONG: 48 x 64 window of Grove2, L=3, K=5, 16 iterations of gqmap_gpu_mixture.m executed; whole state
+# kept after iterations 15 and 16
+LONG_FILE = os.path.join(GOLD, "refsrc_grove2_window_L3K5_it16.npz")
+LONG_FROM, LONG_SHAPE = 15, (48, 64)
+
+
+def _long_case(O):
+    d = np.load(LONG_FILE)
+    I1, I2 = np.asfortranarray(d["I1"].astype(np.float64)), np.asfortranarray(d["I2"].astype(np.float64))
+    Mo, No = I1.shape
+    minu, maxu, minv, maxv = (float(x) for x in d["range"])
+    cfg = O.make_config(Mo, No, 3, 5, lambdas=5.0, epsn=0.001 ** 2, minu=minu, maxu=maxu, minv=minv, maxv=maxv)
+
+    def state(it):
+        g = lambda f: np.array(d["f%d_%s" % (it, f)], order="F")
+        return O.State(g("muu"), g("muv"), g("sigmau"), g("sigmav"), g("pn"), g("rou"), np.ravel(g("w")), alpha=np.ravel(g("alpha")), T=0.0)
+    return d, cfg, I1, I2, state
+
+
+def test_oracle_single_step_from_late_state_on_reference_data(O):
+    d, cfg, I1, I2, state = _long_case(O)
+    k = LONG_FROM
+    VV = O.get_vv(I2)
+    st, ref = state(k), state(k + 1)
+    assert np.abs(st.pn).max() > 0.01 and np.abs(st.rou).max() > 0.5            # the correlation terms are exercised (zero at iteration 1)
+    n, _, stopped, E, dm, ds = O.run(cfg, I1, VV, st, k + 1, 10 ** 6, 1)
+    assert n == 1 and abs(E[0] / d["Energy"][k] - 1) < 1e-12, (E[0], d["Energy"][k])
+    assert abs(dm[0] / float(d["p%d_ptdmu" % (k + 1)]) - 1) < 1e-10 and abs(ds[0] / float(d["p%d_ptdsigma" % (k + 1)]) - 1) < 1e-10
+    for f in ("muu", "muv", "sigu", "sigv", "pn", "rou"):                      # fp64 rounding x the 1/(1-rho^2) factor of the gradients x step
+        _close(getattr(st, f), getattr(ref, f), 1e-9, f)
+    _close(st.alpha, ref.alpha, 1e-15, "alpha")
+    assert I1.shape == LONG_SHAPE and d["Energy"].size == k + 1 and np.all(np.isfinite(d["Energy"]))
+
+
+@pytest.mark.gpu
+def test_cuda_single_step_from_late_state_on_reference_data(pkg, O):
+    from test_gpu_parity import _round_state
+    from test_gpu_full_size import _assert_step_close
+    d, cfg, I1, I2, state = _long_case(O)
+    k = LONG_FROM
+    VV = O.get_vv(I2)
+    before = _round_state(state(k))
+    ref = before.copy()
+    _, _, _, E, dm, ds = O.run(cfg, I1, VV, ref, k + 1, 10 ** 6, 1)           # the oracle from the fp32-rounded state, whole state
+    with pkg.Solver(options_from_cfg(cfg), I1, I2) as s:
+        s.set_state(state_dict(before), it=k + 1, alpha=before.alpha)
+        r = s.step(1)
+        got = s.get_state()
+    print("late state it=%d: Energy rel %.2e (executed source), %.2e (oracle, same fp32 start); ptdmu rel %.2e" % (
+        k + 1, r["Energy"][0] / d["Energy"][k] - 1, r["Energy"][0] / E[0] - 1, r["ptdmu"][0] / dm[0] - 1))
+    assert abs(r["Energy"][0] / E[0] - 1) < 1e-5 and abs(r["Energy"][0] / d["Energy"][k] - 1) < 1e-4        # north_star: 1e-4
+    # mean|G| (:69-70): 1e-4 relative plus the fp32 floor of tests/test_gpu_full_size.py -- this state has sigmas at the 0.01 floor and
+    # correlations at the clamp, where rounding the INPUT to fp32 alone moves mean|dmu| by 1.7e-5 relative (measured with the oracle)
+    prn = (1 - before.pn ** 2)[1:-1, 1:-1]
+    floor_u = 3e-5 * float(np.mean(1.0 / (before.sigu[1:-1, 1:-1] * prn)))
+    assert abs(r["ptdmu"][0] - dm[0]) < 1e-4 * dm[0] + floor_u and abs(r["ptdsigma"][0] - ds[0]) < 1e-4 * ds[0] + floor_u
+    _assert_step_close(got, ref, before, cfg.step0 / (1 + (k + 1) / cfg.step_tau), where="Grove2 window, it=%d" % (k + 1))
+
+
 # ---- host-side files of the drivers' path: readFlowFile.m, legacy/writeFlowFile.m, legacy/flowToColor.m (+ maxFlow) -----------
 def test_host_io_against_executed_source(pkg, O, tmp_path):
     d = np.load(os.path.join(GOLD, "refsrc_host_io.npz"))
