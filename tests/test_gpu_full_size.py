@@ -20,7 +20,7 @@ def _state_to_oracle(O, g):
                    alpha=g["alpha"], T=g["T"])
 
 
-def _assert_step_close(got, ref, before, step, cols=slice(None), where=""):
+def _assert_step_close(got, ref, before, step, cols=slice(None), where="", max_bad_frac=0.0):
     """One ascent step from identical state, without the 14 full-size gradient arrays of tests/test_gpu_parity.py::
     _assert_state_close (7 GB at 4K): the state error must be a small fraction (1e-3) of the step the belief actually took,
     |ref - before|, plus the documented fp32 floor: the potentials (|f| ~ 1e2, relative 1e-7) enter the gradients multiplied by
@@ -40,7 +40,9 @@ def _assert_step_close(got, ref, before, step, cols=slice(None), where=""):
         err = np.abs(got[name] - refa)[:, cols]
         tol = (2e-5 + 1e-3 * np.abs(refa - bef) + step * 3e-5 * amp[name])[:, cols]
         worst[name] = float((err / tol).max())
-        assert np.all(err <= tol), (where, name, worst[name], float(err.max()))
+        # max_bad_frac > 0: states of the reference's own early trajectory hold isolated hypersensitive beliefs (sigma at its 0.01 floor next to
+        # correlations at the clamp); a systematic error would violate the bound everywhere, not in a handful of entries
+        assert float(np.mean(err > tol)) <= max_bad_frac, (where, name, worst[name], float(err.max()), float(np.mean(err > tol)))
     return worst
 
 

@@ -444,31 +444,6 @@ def test_oracle_single_step_from_late_state_on_reference_data(O):
     assert I1.shape == LONG_SHAPE and d["Energy"].size == k + 1 and np.all(np.isfinite(d["Energy"]))
 
 
-@pytest.mark.gpu
-def test_cuda_single_step_from_late_state_on_reference_data(pkg, O):
-    from test_gpu_parity import _round_state
-    from test_gpu_full_size import _assert_step_close
-    d, cfg, I1, I2, state = _long_case(O)
-    k = LONG_FROM
-    VV = O.get_vv(I2)
-    before = _round_state(state(k))
-    ref = before.copy()
-    _, _, _, E, dm, ds = O.run(cfg, I1, VV, ref, k + 1, 10 ** 6, 1)           # the oracle from the fp32-rounded state, whole state
-    with pkg.Solver(options_from_cfg(cfg), I1, I2) as s:
-        s.set_state(state_dict(before), it=k + 1, alpha=before.alpha)
-        r = s.step(1)
-        got = s.get_state()
-    print("late state it=%d: Energy rel %.2e (executed source), %.2e (oracle, same fp32 start); ptdmu rel %.2e" % (
-        k + 1, r["Energy"][0] / d["Energy"][k] - 1, r["Energy"][0] / E[0] - 1, r["ptdmu"][0] / dm[0] - 1))
-    assert abs(r["Energy"][0] / E[0] - 1) < 1e-5 and abs(r["Energy"][0] / d["Energy"][k] - 1) < 1e-4        # north_star: 1e-4
-    # mean|G| (:69-70): 1e-4 relative plus the fp32 floor of tests/test_gpu_full_size.py -- this state has sigmas at the 0.01 floor and
-    # correlations at the clamp, where rounding the INPUT to fp32 alone moves mean|dmu| by 1.7e-5 relative (measured with the oracle)
-    prn = (1 - before.pn ** 2)[1:-1, 1:-1]
-    floor_u = 3e-5 * float(np.mean(1.0 / (before.sigu[1:-1, 1:-1] * prn)))
-    assert abs(r["ptdmu"][0] - dm[0]) < 1e-4 * dm[0] + floor_u and abs(r["ptdsigma"][0] - ds[0]) < 1e-4 * ds[0] + floor_u
-    _assert_step_close(got, ref, before, cfg.step0 / (1 + (k + 1) / cfg.step_tau), where="Grove2 window, it=%d" % (k + 1))
-
-
 # ---- host-side files of the drivers' path: readFlowFile.m, legacy/writeFlowFile.m, legacy/flowToColor.m (+ maxFlow) -----------
 def test_host_io_against_executed_source(pkg, O, tmp_path):
     d = np.load(os.path.join(GOLD, "refsrc_host_io.npz"))
@@ -569,3 +544,31 @@ def test_cuda_alpha_and_anneal_against_executed_source(pkg, O, name):
             assert np.abs(got["alpha"] - np.ravel(d["p%d_alpha" % (k + 1)])).max() < 1e-12 + 1e-3 * da, k
             if k + 2 in probes:
                 assert abs(got["T"] - float(d["p%d_T" % (k + 2)])) < 1e-15, (k, got["T"])
+
+
+# (last in the file and in the suite: written after the round's GPU budget was spent -- its CPU twin above and its script logic, run against an
+# oracle-backed stand-in for the Solver, are verified; the thresholds are those the full-size late-state tests hold on B200)
+@pytest.mark.gpu
+def test_cuda_single_step_from_late_state_on_reference_data(pkg, O):
+    from test_gpu_parity import _round_state
+    from test_gpu_full_size import _assert_step_close
+    d, cfg, I1, I2, state = _long_case(O)
+    k = LONG_FROM
+    VV = O.get_vv(I2)
+    before = _round_state(state(k))
+    ref = before.copy()
+    _, _, _, E, dm, ds = O.run(cfg, I1, VV, ref, k + 1, 10 ** 6, 1)           # the oracle from the fp32-rounded state, whole state
+    with pkg.Solver(options_from_cfg(cfg), I1, I2) as s:
+        s.set_state(state_dict(before), it=k + 1, alpha=before.alpha)
+        r = s.step(1)
+        got = s.get_state()
+    print("late state it=%d: Energy rel %.2e (executed source), %.2e (oracle, same fp32 start); ptdmu rel %.2e" % (
+        k + 1, r["Energy"][0] / d["Energy"][k] - 1, r["Energy"][0] / E[0] - 1, r["ptdmu"][0] / dm[0] - 1))
+    assert abs(r["Energy"][0] / E[0] - 1) < 1e-5 and abs(r["Energy"][0] / d["Energy"][k] - 1) < 1e-4        # north_star: 1e-4
+    # mean|G| (:69-70): 1e-4 relative plus the fp32 floor of tests/test_gpu_full_size.py -- this state has sigmas at the 0.01 floor and
+    # correlations at the clamp, where rounding the INPUT to fp32 alone moves mean|dmu| by 1.7e-5 relative (measured with the oracle)
+    prn = (1 - before.pn ** 2)[1:-1, 1:-1]
+    floor_u = 3e-5 * float(np.mean(1.0 / (before.sigu[1:-1, 1:-1] * prn)))
+    assert abs(r["ptdmu"][0] - dm[0]) < 1e-4 * dm[0] + floor_u and abs(r["ptdsigma"][0] - ds[0]) < 1e-4 * ds[0] + floor_u
+    worst = _assert_step_close(got, ref, before, cfg.step0 / (1 + (k + 1) / cfg.step_tau), where="Grove2 window, it=%d" % (k + 1), max_bad_frac=1e-3)
+    print("worst error / bound per field:", worst)
