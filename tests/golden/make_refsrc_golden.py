@@ -268,7 +268,12 @@ REAL_CASES = {
 
 # A longer run, for single steps from LATER states of the reference's own trajectory on its own data (at iteration 1 every correlation is
 # still zero): a 48 x 64 window of Grove2, L=3, K=5, 16 iterations, the whole state kept after iterations 15 and 16 (~30 minutes)
-REAL_LONG = {"grove2_window_L3K5_it16": ("Grove2", "gqmap_gpu_mixture", 3, 5, FULL_C, 2025, 4, (208, 256, 280, 344), True, 16, (15, 16))}
+REAL_LONG = {
+    "grove2_window_L3K5_it16": ("Grove2", "gqmap_gpu_mixture", 3, 5, FULL_C, 2025, 4, (208, 256, 280, 344), True, 16, (15, 16)),
+    # the super-pixel variant (64 x 80 window of Venus = 16 x 20 beliefs, v range [0, 0]) and the driver's K=9 (32 x 48 window of Dimetrodon, L=2)
+    "venus_super_window_L3K5_it12": ("Venus", "gqmap_gpuSuper_mix_entropy", 3, 5, SUPER_C, 2026, 2, (120, 184, 140, 220), True, 12, (11, 12)),
+    "dimetrodon_window_L2K9_it8": ("Dimetrodon", "gqmap_gpu_mixture", 2, 9, FULL_C, 2027, 4, (170, 202, 230, 278), True, 8, (7, 8)),
+}
 
 
 def run_real(name, crop=None):

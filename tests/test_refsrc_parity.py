@@ -412,36 +412,42 @@ def test_cuda_steps_against_executed_source_on_reference_data(pkg, O, name):
 # ---- single steps from LATER states of the reference's own trajectory on its own data (at iteration 1 every correlation is still zero) ----
 # tests/golden/make_refsrc_golden.py::REAL_LONG: 48 x 64 window of Grove2, L=3, K=5, 16 iterations of gqmap_gpu_mixture.m executed; whole state
 # kept after iterations 15 and 16
-LONG_FILE = os.path.join(GOLD, "refsrc_grove2_window_L3K5_it16.npz")
-LONG_FROM, LONG_SHAPE = 15, (48, 64)
+# name -> (super-pixel variant, L, K, lambdas, T, drate, iteration whose state the step starts from, frame shape)
+REAL_LATE = {
+    "grove2_window_L3K5_it16": (False, 3, 5, 5.0, 0.0, 0.5, 15, (48, 64)),
+}
+LATE_FILE = {name: os.path.join(GOLD, "refsrc_%s.npz" % name) for name in REAL_LATE}
 
 
-def _long_case(O):
-    d = np.load(LONG_FILE)
+def _long_case(O, name="grove2_window_L3K5_it16"):
+    sup, L, K, lambdas, T, drate, k, shape = REAL_LATE[name]
+    d = np.load(LATE_FILE[name])
     I1, I2 = np.asfortranarray(d["I1"].astype(np.float64)), np.asfortranarray(d["I2"].astype(np.float64))
     Mo, No = I1.shape
     minu, maxu, minv, maxv = (float(x) for x in d["range"])
-    cfg = O.make_config(Mo, No, 3, 5, lambdas=5.0, epsn=0.001 ** 2, minu=minu, maxu=maxu, minv=minv, maxv=maxv)
+    cfg = O.make_config(Mo, No, L, K, super=sup, lambdas=lambdas, epsn=0.001 ** 2, minu=minu, maxu=maxu, minv=minv, maxv=maxv, drate=drate)
 
     def state(it):
         g = lambda f: np.array(d["f%d_%s" % (it, f)], order="F")
-        return O.State(g("muu"), g("muv"), g("sigmau"), g("sigmav"), g("pn"), g("rou"), np.ravel(g("w")), alpha=np.ravel(g("alpha")), T=0.0)
+        return O.State(g("muu"), g("muv"), g("sigmau"), g("sigmav"), g("pn"), g("rou"), np.ravel(g("w")), alpha=np.ravel(g("alpha")), T=T)
     return d, cfg, I1, I2, state
 
 
-def test_oracle_single_step_from_late_state_on_reference_data(O):
-    d, cfg, I1, I2, state = _long_case(O)
-    k = LONG_FROM
+@pytest.mark.parametrize("name", sorted(REAL_LATE))
+def test_oracle_single_step_from_late_state_on_reference_data(O, name):
+    sup, L, K, lambdas, T, drate, k, shape = REAL_LATE[name]
+    d, cfg, I1, I2, state = _long_case(O, name)
     VV = O.get_vv(I2)
     st, ref = state(k), state(k + 1)
-    assert np.abs(st.pn).max() > 0.01 and np.abs(st.rou).max() > 0.5            # the correlation terms are exercised (zero at iteration 1)
+    assert np.abs(st.pn).max() > 0.01 and np.abs(st.rou).max() > 0.5          # the correlation terms are exercised (zero at iteration 1)
     n, _, stopped, E, dm, ds = O.run(cfg, I1, VV, st, k + 1, 10 ** 6, 1)
     assert n == 1 and abs(E[0] / d["Energy"][k] - 1) < 1e-12, (E[0], d["Energy"][k])
     assert abs(dm[0] / float(d["p%d_ptdmu" % (k + 1)]) - 1) < 1e-10 and abs(ds[0] / float(d["p%d_ptdsigma" % (k + 1)]) - 1) < 1e-10
+    assert st.T == float(d["p%d_T" % (k + 1)]) == T
     for f in ("muu", "muv", "sigu", "sigv", "pn", "rou"):                      # fp64 rounding x the 1/(1-rho^2) factor of the gradients x step
         _close(getattr(st, f), getattr(ref, f), 1e-9, f)
     _close(st.alpha, ref.alpha, 1e-15, "alpha")
-    assert I1.shape == LONG_SHAPE and d["Energy"].size == k + 1 and np.all(np.isfinite(d["Energy"]))
+    assert I1.shape == shape and d["Energy"].size == k + 1 and np.all(np.isfinite(d["Energy"]))
 
 
 # ---- host-side files of the drivers' path: readFlowFile.m, legacy/writeFlowFile.m, legacy/flowToColor.m (+ maxFlow) -----------
@@ -552,8 +558,8 @@ def test_cuda_alpha_and_anneal_against_executed_source(pkg, O, name):
 def test_cuda_single_step_from_late_state_on_reference_data(pkg, O):
     from test_gpu_parity import _round_state
     from test_gpu_full_size import _assert_step_close
-    d, cfg, I1, I2, state = _long_case(O)
-    k = LONG_FROM
+    d, cfg, I1, I2, state = _long_case(O, "grove2_window_L3K5_it16")
+    k = REAL_LATE["grove2_window_L3K5_it16"][6]
     VV = O.get_vv(I2)
     before = _round_state(state(k))
     ref = before.copy()
