@@ -415,6 +415,9 @@ def test_cuda_steps_against_executed_source_on_reference_data(pkg, O, name):
 # name -> (super-pixel variant, L, K, lambdas, T, drate, iteration whose state the step starts from, frame shape)
 REAL_LATE = {
     "grove2_window_L3K5_it16": (False, 3, 5, 5.0, 0.0, 0.5, 15, (48, 64)),
+    # the super-pixel variant (64 x 80 window of Venus = 16 x 20 beliefs, v range [0, 0], T = 0.2) and the driver's K=9 (32 x 48 window of Dimetrodon, L=2)
+    "venus_super_window_L3K5_it12": (True, 3, 5, 16.0, 0.2, 0.75, 11, (64, 80)),
+    "dimetrodon_window_L2K9_it8": (False, 2, 9, 5.0, 0.0, 0.5, 7, (32, 48)),
 }
 LATE_FILE = {name: os.path.join(GOLD, "refsrc_%s.npz" % name) for name in REAL_LATE}
 
